@@ -1,0 +1,147 @@
+/* b2m.h -- C ABI of the B200-native Marlin prover hot path.
+ *
+ * The reference (arkworks-rs/marlin) has no FFI; its seam is the generic parameter
+ * `PC: PolynomialCommitment<F, DensePolynomial<F>>` of `Marlin<F, PC, FS>`
+ * (reference src/lib.rs:64-71) and, one level down, the two upstream free functions every
+ * commit/open and every AHP round bottoms out in.  Each entry point below names the
+ * reference interface it replaces.  A Rust shim binding these turns the
+ * library into a drop-in `PC` / prover backend.
+ *
+ * Conventions
+ *   - Field elements cross the boundary exactly as ark-ff 0.3 stores them: little-endian
+ *     u64 limbs in MONTGOMERY form (Fr: 4 limbs; Fq: 6 limbs for BLS12-381, 4 for BN254),
+ *     except MSM scalars, which are canonical integers (`into_repr()`), as in
+ *     `VariableBaseMSM::multi_scalar_mul(&[G::Affine], &[BigInt])`.
+ *   - A G1 affine point is x||y (2*LQ u64 limbs, Montgomery); the point at infinity is
+ *     encoded as x = y = 0 (never a curve point since b != 0).
+ *   - Every function returns B2M_OK or an error code; b2m_last_error() gives the message.
+ *     The library never aborts the host process and never falls back to the CPU.
+ *   - A b2m_ctx owns one device and one stream; it is not thread-safe, distinct contexts
+ *     are independent.  All calls are synchronous at return.
+ */
+#ifndef B2M_H
+#define B2M_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  B2M_OK = 0,
+  B2M_ERR_INVALID_ARG = 1,
+  B2M_ERR_INDEX_TOO_LARGE = 2,          /* reference src/error.rs:7  Error::IndexTooLarge */
+  B2M_ERR_INSTANCE_MISMATCH = 3,        /* reference src/ahp/mod.rs:276 InstanceDoesNotMatchIndex */
+  B2M_ERR_INVALID_PUBLIC_INPUT_LEN = 4, /* reference src/ahp/mod.rs:274 InvalidPublicInputLength */
+  B2M_ERR_NON_SQUARE = 5,               /* reference src/ahp/mod.rs:278 NonSquareMatrix */
+  B2M_ERR_DEGREE_TOO_LARGE = 6,         /* SynthesisError::PolynomialDegreeTooLarge / PC degree errors */
+  B2M_ERR_MISSING_RNG = 7,              /* [U ark-poly-commit Error::MissingRng] */
+  B2M_ERR_CUDA = 8,
+  B2M_ERR_NCCL = 9,
+  B2M_ERR_UNSUPPORTED = 10
+};
+
+enum { B2M_CURVE_BLS12_381 = 0, B2M_CURVE_BN254 = 1 };
+enum { B2M_PC_MARLIN_KZG10 = 0, B2M_PC_SONIC_KZG10 = 1 };
+/* stream ciphers behind `RngCore`: rand 0.8 StdRng (= ChaCha12, `ark_std::test_rng`) and
+ * rand_chacha::ChaChaRng (= ChaCha20). */
+enum { B2M_RNG_CHACHA12 = 12, B2M_RNG_CHACHA20 = 20, B2M_RNG_CHACHA8 = 8 };
+
+typedef struct b2m_ctx b2m_ctx;
+typedef struct b2m_srs b2m_srs;
+typedef struct b2m_index b2m_index;
+
+const char* b2m_last_error(void);
+const char* b2m_version(void);
+
+/* One context per GPU. */
+int b2m_ctx_create(int device, b2m_ctx** out);
+void b2m_ctx_destroy(b2m_ctx* ctx);
+/* Number of kernel launches issued through this context so far. */
+unsigned long long b2m_ctx_launches(const b2m_ctx* ctx);
+
+/* ---- Level 0: kernel ABI ------------------------------------------------------------- */
+
+/* Replaces `Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place(&mut Vec<F>)`
+ * [U ark-poly 0.3 domain/radix2]; call sites reference src/ahp/prover.rs:321-326,350-353,
+ * 359,365,427,467,488,532-545,655,681,685.  `data` is a HOST buffer of 2^log_n Fr elements
+ * (natural order in and out); inverse != 0 also scales by n^-1; coset != 0 uses the coset
+ * g*H with g = F::multiplicative_generator(). */
+int b2m_ntt(b2m_ctx* ctx, int curve, uint64_t* data, unsigned log_n, int inverse, int coset);
+
+/* Replaces `VariableBaseMSM::multi_scalar_mul(bases, scalars)` [U ark-ec 0.3 msm/variable_base.rs].
+ * One-shot form: uploads `bases`, builds the window tables, runs the MSM, frees everything.
+ * out_xy receives the affine result (Montgomery), *out_is_inf is set for the identity. */
+int b2m_msm_g1(b2m_ctx* ctx, int curve, const uint64_t* bases_xy, const uint64_t* scalars, size_t n,
+               uint64_t* out_xy, int* out_is_inf);
+
+/* Device-resident committer key: the G1 powers of `PC::UniversalParams` (what `PC::trim`,
+ * reference src/lib.rs:115-121, slices).  powers_of_g: n_g affine points (beta^i G);
+ * powers_of_gamma_g: n_gamma affine points (beta^i gamma G) used for hiding.
+ * window_bits = 0 picks the window from n_g.  The library precomputes 2^(c*w) multiples of
+ * every power (HBM for doublings) so every later MSM over any contiguous slice is one
+ * bucket pass. */
+int b2m_srs_create(b2m_ctx* ctx, int curve, const uint64_t* powers_of_g, size_t n_g,
+                   const uint64_t* powers_of_gamma_g, size_t n_gamma, int window_bits, b2m_srs** out);
+void b2m_srs_destroy(b2m_srs* srs);
+size_t b2m_srs_size(const b2m_srs* srs);
+int b2m_srs_window_bits(const b2m_srs* srs);
+/* MSM over the slice powers_of_g[base_off .. base_off+n) with canonical host scalars. */
+int b2m_srs_msm(b2m_srs* srs, size_t base_off, const uint64_t* scalars, size_t n, uint64_t* out_xy,
+                int* out_is_inf);
+/* Test-SRS generator (replaces the G1 half of `KZG10::setup`, [U ark-poly-commit kzg10]):
+ * fills powers_of_g[i] = beta^i * g for i < n on the GPU.  beta is a canonical Fr. */
+int b2m_g1_powers(b2m_ctx* ctx, int curve, const uint64_t* g_xy, const uint64_t* beta, size_t n,
+                  uint64_t* out_powers_xy);
+
+/* ---- Level 2: prover ABI ---------------------------------------------------------------- */
+
+/* R1CS matrix in CSR form, as `ConstraintSystem::to_matrices()` yields it
+ * (reference src/ahp/indexer.rs:81 `Matrix<F> = Vec<Vec<(F, usize)>>`): row r holds entries
+ * [row_ptr[r], row_ptr[r+1]); coeff is Montgomery Fr (4 u64 each). */
+typedef struct {
+  const uint64_t* row_ptr; /* num_constraints + 1 */
+  const uint64_t* col;     /* nnz column (variable) indices */
+  const uint64_t* coeff;   /* nnz * 4 limbs */
+} b2m_matrix;
+
+/* Replaces `Marlin::index` (reference src/lib.rs:100-148): AHP indexer
+ * (src/ahp/indexer.rs:151-234, src/ahp/constraint_systems.rs:125-262) + `PC::trim` +
+ * commitment to the six index polynomials.  The matrices must already be padded/squared
+ * (num_constraints == num_variables) as `make_matrices_square_for_indexer` leaves them.
+ * vk_bytes receives `IndexVerifierKey::write` (ToBytes) output: index_info || index_comms. */
+int b2m_index_create(b2m_srs* srs, int pc_variant, size_t num_constraints, size_t num_variables,
+                     size_t num_instance_variables, const b2m_matrix* a, const b2m_matrix* b,
+                     const b2m_matrix* c, b2m_index** out);
+void b2m_index_destroy(b2m_index* idx);
+/* Serialized `index_vk` as the transcript sees it (ToBytes, reference src/data_structures.rs:36-43). */
+int b2m_index_vk_bytes(const b2m_index* idx, uint8_t* out, size_t cap, size_t* len);
+/* Commitments to the index polynomials (affine x||y Montgomery, 6 points). */
+int b2m_index_comms(const b2m_index* idx, uint64_t* out_xy);
+
+/* The caller's `zk_rng: &mut R` (reference src/lib.rs:154).  A ChaCha block RNG is described by
+ * its key and word position so the mask polynomial (3|H| draws, src/ahp/prover.rs:371) can
+ * be sampled on the device bit-exactly; word_pos is updated to the position after the call. */
+typedef struct {
+  int kind;          /* B2M_RNG_CHACHA* */
+  uint8_t key[32];
+  uint64_t word_pos; /* number of 32-bit words already consumed from the stream */
+} b2m_rng;
+
+/* Replaces `Marlin::prove` (reference src/lib.rs:151-311).  formatted_input: the instance
+ * assignment including the leading one (|X| elements); witness: the witness assignment
+ * (num_variables - |X| elements), both Montgomery Fr.  proof receives the
+ * `CanonicalSerialize` bytes of `Proof<F, PC>` (reference src/data_structures.rs:100-110). */
+int b2m_prove(b2m_index* idx, const uint64_t* formatted_input, size_t n_input,
+              const uint64_t* witness, size_t n_witness, b2m_rng* zk_rng, uint8_t* proof,
+              size_t cap, size_t* proof_len);
+
+/* Per-phase device timings of the last b2m_prove on this index (milliseconds), labelled
+ * with the reference's own timer names (ark_std start_timer! labels). */
+int b2m_prove_timings(const b2m_index* idx, char* json, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2M_H */

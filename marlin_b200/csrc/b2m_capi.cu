@@ -1,0 +1,95 @@
+// extern "C" boundary of libb2m.so (declared in include/b2m.h).  Level 0: NTT / MSM / SRS.
+// The prover-level entry points live in prover.cu.
+#include "capi_types.cuh"
+
+namespace b2m {
+thread_local std::string g_last_error;
+}
+
+using namespace b2m;
+
+extern "C" {
+
+const char* b2m_last_error(void) { return g_last_error.c_str(); }
+const char* b2m_version(void) { return "b2m 0.1 (sm_100a)"; }
+
+int b2m_ctx_create(int device, b2m_ctx** out) {
+  return guard([&] {
+    B2M_REQUIRE(out != nullptr, B2M_ERR_INVALID_ARG, "out is null");
+    *out = new b2m_ctx(device);
+  });
+}
+
+void b2m_ctx_destroy(b2m_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cx.device);
+  cudaStreamSynchronize(ctx->cx.stream);
+  delete ctx;
+}
+
+unsigned long long b2m_ctx_launches(const b2m_ctx* ctx) { return ctx ? ctx->cx.launches : 0; }
+
+int b2m_ntt(b2m_ctx* ctx, int curve, uint64_t* data, unsigned log_n, int inverse, int coset) {
+  return guard([&] {
+    B2M_REQUIRE(ctx && data, B2M_ERR_INVALID_ARG, "null argument");
+    ctx->cx.use();
+    if (curve == B2M_CURVE_BLS12_381) ctx->ntt_bls().run_host(data, log_n, inverse != 0, coset != 0);
+    else if (curve == B2M_CURVE_BN254) ctx->ntt_bn().run_host(data, log_n, inverse != 0, coset != 0);
+    else throw Error(B2M_ERR_INVALID_ARG, "unknown curve id");
+  });
+}
+
+int b2m_srs_create(b2m_ctx* ctx, int curve, const uint64_t* powers_of_g, size_t n_g, const uint64_t* powers_of_gamma_g,
+                   size_t n_gamma, int window_bits, b2m_srs** out) {
+  return guard([&] {
+    B2M_REQUIRE(ctx && powers_of_g && out, B2M_ERR_INVALID_ARG, "null argument");
+    B2M_REQUIRE(curve == B2M_CURVE_BLS12_381 || curve == B2M_CURVE_BN254, B2M_ERR_INVALID_ARG, "unknown curve id");
+    ctx->cx.use();
+    *out = new b2m_srs(ctx, curve, powers_of_g, n_g, powers_of_gamma_g, n_gamma, window_bits);
+  });
+}
+
+void b2m_srs_destroy(b2m_srs* srs) {
+  if (!srs) return;
+  srs->ctx->cx.use();
+  cudaStreamSynchronize(srs->ctx->cx.stream);
+  delete srs;
+}
+
+size_t b2m_srs_size(const b2m_srs* srs) { return srs ? srs->n_g : 0; }
+int b2m_srs_window_bits(const b2m_srs* srs) { return srs ? srs->window_bits() : 0; }
+
+int b2m_srs_msm(b2m_srs* srs, size_t base_off, const uint64_t* scalars, size_t n, uint64_t* out_xy, int* out_is_inf) {
+  return guard([&] {
+    B2M_REQUIRE(srs && out_xy && (scalars || n == 0), B2M_ERR_INVALID_ARG, "null argument");
+    srs->ctx->cx.use();
+    if (srs->curve == B2M_CURVE_BLS12_381) srs->bls->run_host(base_off, scalars, n, out_xy, out_is_inf);
+    else srs->bn->run_host(base_off, scalars, n, out_xy, out_is_inf);
+  });
+}
+
+int b2m_msm_g1(b2m_ctx* ctx, int curve, const uint64_t* bases_xy, const uint64_t* scalars, size_t n, uint64_t* out_xy,
+               int* out_is_inf) {
+  b2m_srs* srs = nullptr;
+  if (n == 0) {
+    if (out_is_inf) *out_is_inf = 1;
+    return B2M_OK;
+  }
+  int rc = b2m_srs_create(ctx, curve, bases_xy, n, nullptr, 0, 0, &srs);
+  if (rc != B2M_OK) return rc;
+  rc = b2m_srs_msm(srs, 0, scalars, n, out_xy, out_is_inf);
+  b2m_srs_destroy(srs);
+  return rc;
+}
+
+int b2m_g1_powers(b2m_ctx* ctx, int curve, const uint64_t* g_xy, const uint64_t* beta, size_t n, uint64_t* out_powers_xy) {
+  return guard([&] {
+    B2M_REQUIRE(ctx && g_xy && beta && out_powers_xy, B2M_ERR_INVALID_ARG, "null argument");
+    ctx->cx.use();
+    if (curve == B2M_CURVE_BLS12_381) Msm<FrBls, FqBls>::g1_powers_host(ctx->cx, g_xy, beta, n, out_powers_xy);
+    else if (curve == B2M_CURVE_BN254) Msm<FrBn, FqBn>::g1_powers_host(ctx->cx, g_xy, beta, n, out_powers_xy);
+    else throw Error(B2M_ERR_INVALID_ARG, "unknown curve id");
+  });
+}
+
+}  // extern "C"

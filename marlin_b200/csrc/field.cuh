@@ -99,6 +99,7 @@ B2M_HD void madc_n_rshift(uint32_t* acc, const uint32_t* a, uint32_t b) {
 
 template <class P>
 struct Fp {
+  using Params = P;
   static constexpr int N = P::N;
   uint32_t l[N];
 

@@ -1,0 +1,2 @@
+#include "msm_impl.cuh"
+namespace b2m { template struct Msm<FrBls, FqBls>; }

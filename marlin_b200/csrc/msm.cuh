@@ -1,0 +1,65 @@
+// Variable-base multi-scalar multiplication over G1 for sm_100a.
+//
+// Replaces ark-ec 0.3 `VariableBaseMSM::multi_scalar_mul(&[G::Affine], &[BigInt])`
+// [U ark-ec src/msm/variable_base.rs] behind `KZG10::commit` / `KZG10::open`, i.e. behind every
+// `PC::commit` and `PC::open_combinations` of the prover [R src/lib.rs:172,193,213,292].
+//
+// The reference runs Pippenger with ~17 windows of c = ln(n)+2 bits, one rayon task per
+// window, 2^c-1 Jacobian buckets each, a running-sum reduction per window and c doublings
+// between windows.  The B200 design trades HBM capacity for all of the doublings and all but
+// one of the bucket sets: the bases are the FIXED powers of the SRS, so at key-load time we
+// store 2^(c*w) * P_i for every window w (W tables, W*96 B per power; 5.2 GB for 2^22 powers
+// at c = 20).  An MSM is then ONE bucket problem: every (scalar, window) signed digit d sends
+// table[w][i] (negated if d < 0) to bucket |d|, and the answer is sum_b b * B_b.
+//   1. digits:      Montgomery scalar -> canonical -> W signed c-bit digits, histogram
+//   2. scan:        exclusive prefix sum of the 2^(c-1) bucket sizes
+//   3. scatter:     counting-sort the (window, index, sign) references by bucket
+//   4. accumulate:  one thread per bucket, XYZZ mixed additions (the dominant kernel)
+//   5. reduce:      hierarchical weighted sum  sum_b (b+1) B_b  (segment running sums)
+// The result is a unique group element, compared with the oracle in affine form.
+#pragma once
+#include "common.cuh"
+#include "curve.cuh"
+
+namespace b2m {
+
+constexpr int MSM_MIN_WINDOW = 8;  // 5 window-id bits in a reference: ceil(256 / c) <= 32
+constexpr int MSM_IDX_BITS = 26;  // point index bits in a sorted reference
+constexpr int MSM_SEG = 16;       // segment length of the bucket reduction
+constexpr int MSM_RED_THREADS = 128;
+constexpr uint32_t MSM_NO_DIGIT = 0xffffffffu;
+
+struct MsmLevel {
+  const void* partials;  // XYZZ[count]: per-block T0 sums of this level
+  uint32_t count;
+  uint32_t log_l;        // log2 of this level's segment length
+};
+constexpr int MSM_MAX_LEVELS = 8;
+struct MsmLevels {
+  MsmLevel lv[MSM_MAX_LEVELS];
+  int n;
+};
+
+template <class Fr, class Fq>
+struct Msm {
+  Ctx* ctx;
+  size_t n_srs = 0;
+  int c = 0, W = 0;
+  DBuf<Affine<Fq>> tables;  // [W][n_srs]:  tables[w * n_srs + i] = 2^(c*w) * P_i
+
+  static int pick_window(size_t n);
+  // Upload the powers and build the window tables (key-load time).
+  Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, int window_bits);
+
+  // sum_i scalars[i] * powers[base_off + i] (+ the `extra` XYZZ terms) -> out_xyzz / out_affine on
+  // the device.  `scalars` is a device array, Montgomery form if mont, canonical otherwise.
+  void run(const Fr* scalars, bool mont, size_t n, size_t base_off, const XYZZ<Fq>* extra, int n_extra, XYZZ<Fq>* out_xyzz,
+           Affine<Fq>* out_affine);
+  // sum_i scalars[i] * bases[i] for a handful of terms (n <= 4096): hiding commitments.
+  void run_small(const Affine<Fq>* bases, const Fr* scalars, bool mont, int n, XYZZ<Fq>* out_xyzz);
+  // Level-0 ABI bodies (include/b2m.h): host scalars in, host affine point out.
+  void run_host(size_t base_off, const uint64_t* scalars, size_t n, uint64_t* out_xy, int* out_is_inf);
+  static void g1_powers_host(Ctx& cx, const uint64_t* g_xy, const uint64_t* beta, size_t n, uint64_t* out);
+};
+
+}  // namespace b2m
