@@ -78,12 +78,15 @@ int b2m_msm_g1(b2m_ctx* ctx, int curve, const uint64_t* bases_xy, const uint64_t
 
 /* Device-resident committer key: the G1 powers of `PC::UniversalParams` (what `PC::trim`,
  * reference src/lib.rs:115-121, slices).  powers_of_g: n_g affine points (beta^i G);
- * powers_of_gamma_g: n_gamma affine points (beta^i gamma G) used for hiding.
- * window_bits = 0 picks the window from n_g.  The library precomputes 2^(c*w) multiples of
+ * powers_of_gamma_g: n_gamma affine points beta^(gamma_indices[k]) gamma G used for hiding
+ * (`UniversalParams::powers_of_gamma_g` is a BTreeMap<usize, G1Affine> upstream; Marlin's PC needs
+ * indices 0..=2, Sonic's additionally max_degree - bound + 0..=2 per enforced bound);
+ * gamma_indices == NULL means 0..n_gamma-1.  window_bits = 0 picks the window from n_g.  The library precomputes 2^(c*w) multiples of
  * every power (HBM for doublings) so every later MSM over any contiguous slice is one
  * bucket pass. */
 int b2m_srs_create(b2m_ctx* ctx, int curve, const uint64_t* powers_of_g, size_t n_g,
-                   const uint64_t* powers_of_gamma_g, size_t n_gamma, int window_bits, b2m_srs** out);
+                   const uint64_t* powers_of_gamma_g, const uint64_t* gamma_indices, size_t n_gamma,
+                   int window_bits, b2m_srs** out);
 void b2m_srs_destroy(b2m_srs* srs);
 size_t b2m_srs_size(const b2m_srs* srs);
 int b2m_srs_window_bits(const b2m_srs* srs);

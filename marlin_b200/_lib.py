@@ -55,7 +55,7 @@ def lib():
         L.b2m_ctx_launches.restype = ctypes.c_ulonglong
         L.b2m_ntt.argtypes = [vp, ci, vp, ctypes.c_uint, ci, ci]
         L.b2m_msm_g1.argtypes = [vp, ci, vp, vp, sz, vp, P(ci)]
-        L.b2m_srs_create.argtypes = [vp, ci, vp, sz, vp, sz, ci, P(vp)]
+        L.b2m_srs_create.argtypes = [vp, ci, vp, sz, vp, vp, sz, ci, P(vp)]
         L.b2m_srs_destroy.argtypes = [vp]
         L.b2m_srs_destroy.restype = None
         L.b2m_srs_size.argtypes = [vp]

@@ -1,0 +1,173 @@
+"""Host-side mirror of the reference's public API for the accelerated path:
+`Marlin::<F, PC, FS>::{universal_setup, index, prove}` [reference src/lib.rs:79-311] with
+F in {BLS12-381 Fr, BN254 Fr}, PC in {MarlinKZG10, SonicKZG10}, FS = SimpleHashFiatShamirRng<Blake2s, ChaChaRng>.
+Every call lands in libb2m.so (include/b2m.h); nothing here computes on the CPU beyond marshalling.
+
+`verify` is not accelerated and not shipped by this package; proofs are
+`CanonicalSerialize` bytes that the reference's `Marlin::verify` consumes.
+"""
+import ctypes
+import json
+
+import numpy as np
+
+from . import _lib, fields
+
+PC_IDS = {"marlin_kzg10": _lib.PC_MARLIN_KZG10, "sonic_kzg10": _lib.PC_SONIC_KZG10}
+
+
+class Context:
+    """One GPU (b2m_ctx)."""
+
+    def __init__(self, device=0):
+        self.handle = ctypes.c_void_p()
+        _lib.check(_lib.lib().b2m_ctx_create(device, ctypes.byref(self.handle)))
+
+    def launches(self):
+        return int(_lib.lib().b2m_ctx_launches(self.handle))
+
+    def close(self):
+        if self.handle:
+            _lib.lib().b2m_ctx_destroy(self.handle)
+            self.handle = None
+
+
+class ZkRng:
+    """The caller's `zk_rng` as a ChaCha stream position (ark_std::test_rng() = ChaCha12 with a fixed seed)."""
+    TEST_RNG_SEED = bytes([1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0] + [0] * 16)
+
+    def __init__(self, seed=None, rounds=12, word_pos=0):
+        self.c = _lib.Rng()
+        self.c.kind = rounds
+        seed = self.TEST_RNG_SEED if seed is None else bytes(seed)
+        assert len(seed) == 32
+        ctypes.memmove(self.c.key, seed, 32)
+        self.c.word_pos = word_pos
+
+    @property
+    def word_pos(self):
+        return int(self.c.word_pos)
+
+
+class UniversalSRS:
+    """`PC::UniversalParams`, device resident (b2m_srs): G1 powers + the gamma powers the PC needs."""
+
+    def __init__(self, ctx, curve_id, handle, max_degree, powers_limbs):
+        self.ctx, self.curve_id, self.handle, self.max_degree = ctx, curve_id, handle, max_degree
+        self.powers_limbs = powers_limbs
+
+    def close(self):
+        if self.handle:
+            _lib.lib().b2m_srs_destroy(self.handle)
+            self.handle = None
+
+
+class IndexProverKey:
+    def __init__(self, srs, handle, r1cs, pc):
+        self.srs, self.handle, self.pc = srs, handle, pc
+        self.num_constraints, self.num_variables = r1cs.num_constraints, r1cs.num_variables
+        L = _lib.lib()
+        n = ctypes.c_size_t(0)
+        _lib.check(L.b2m_index_vk_bytes(handle, None, 0, ctypes.byref(n)))
+        buf = (ctypes.c_uint8 * n.value)()
+        _lib.check(L.b2m_index_vk_bytes(handle, buf, n.value, ctypes.byref(n)))
+        self.vk_bytes = bytes(buf)
+        lq = _lib.LIMBS[srs.curve_id][1]
+        self.index_comms = np.zeros((6, 2 * lq), dtype=np.uint64)
+        _lib.check(L.b2m_index_comms(handle, _lib.ptr(self.index_comms)))
+
+    def timings(self):
+        buf = ctypes.create_string_buffer(4096)
+        _lib.check(_lib.lib().b2m_prove_timings(self.handle, buf, 4096))
+        return json.loads(buf.value.decode() or "{}")
+
+    def close(self):
+        if self.handle:
+            _lib.lib().b2m_index_destroy(self.handle)
+            self.handle = None
+
+
+def max_degree(num_constraints, num_variables, num_non_zero):
+    """`AHPForR1CS::max_degree` [reference src/ahp/mod.rs:71-93]"""
+    def p2(n):
+        s = 1
+        while s < n:
+            s *= 2
+        return s
+    h = p2(max(num_variables, num_constraints))
+    k = p2(num_non_zero)
+    return max(2 * h + 1 - 2, 3 * h + 2 - 3, h, h, k - 1)
+
+
+class Marlin:
+    """`Marlin<F, PC, FS>` for one curve and PC scheme on one GPU."""
+
+    def __init__(self, curve="bls12_381", pc="marlin_kzg10", device=0, ctx=None):
+        self.curve_id = fields.CURVE_IDS[curve]
+        self.pc = PC_IDS[pc]
+        self.ctx = ctx or Context(device)
+
+    # -- universal_setup ---------------------------------------------------------------------------
+    def universal_setup(self, num_constraints, num_variables, num_non_zero, beta, g=None, gamma=7, degree_bounds=(),
+                        window_bits=0):
+        """[reference src/lib.rs:79-96] with an explicit trapdoor: an insecure test SRS exactly like the
+        reference's `universal_setup(.., test_rng)`, generated on the GPU.  `degree_bounds`: bounds whose
+        shifted gamma powers SonicKZG10 will need (ignored by MarlinKZG10)."""
+        md = max_degree(num_constraints, num_variables, num_non_zero)
+        return self.srs_from_trapdoor(md, beta, g, gamma, degree_bounds, window_bits)
+
+    def srs_from_trapdoor(self, md, beta, g=None, gamma=7, degree_bounds=(), window_bits=0):
+        L = _lib.lib()
+        cid = self.curve_id
+        lq = _lib.LIMBS[cid][1]
+        g = g or fields.G1_GENERATOR[cid]
+        r = fields.FR_MODULUS[cid]
+        g_l = _lib.ints_to_limbs([fields.fq_to_mont(cid, g[0]), fields.fq_to_mont(cid, g[1])], lq).reshape(1, 2 * lq)
+        beta_l = _lib.ints_to_limbs([beta % r], 4)
+        powers = np.zeros((md + 1, 2 * lq), dtype=np.uint64)
+        _lib.check(L.b2m_g1_powers(self.ctx.handle, cid, _lib.ptr(g_l), _lib.ptr(beta_l), md + 1, _lib.ptr(powers)))
+        # gamma powers: gamma * beta^i * g = one-term MSMs of the G1 powers
+        idx = [0, 1, 2]
+        for d in sorted(set(degree_bounds)):
+            idx += [md - d + i for i in range(3) if md - d + i <= md]
+        idx = sorted(set(idx))
+        gam = np.zeros((len(idx), 2 * lq), dtype=np.uint64)
+        gamma_l = _lib.ints_to_limbs([gamma % r], 4)
+        inf = ctypes.c_int(0)
+        for k, i in enumerate(idx):
+            base = np.ascontiguousarray(powers[i:i + 1])
+            _lib.check(L.b2m_msm_g1(self.ctx.handle, cid, _lib.ptr(base), _lib.ptr(gamma_l), 1, _lib.ptr(gam[k]), ctypes.byref(inf)))
+        return self.srs_from_points(powers, gam, idx, window_bits)
+
+    def srs_from_points(self, powers_limbs, gamma_limbs, gamma_indices, window_bits=0):
+        """Upload an existing SRS (affine Montgomery limbs, as ark-ff stores them)."""
+        L = _lib.lib()
+        h = ctypes.c_void_p()
+        gi = np.asarray(gamma_indices, dtype=np.uint64)
+        powers_limbs = np.ascontiguousarray(powers_limbs)
+        gamma_limbs = np.ascontiguousarray(gamma_limbs)
+        _lib.check(L.b2m_srs_create(self.ctx.handle, self.curve_id, _lib.ptr(powers_limbs), len(powers_limbs), _lib.ptr(gamma_limbs),
+                                    _lib.ptr(gi), len(gi), window_bits, ctypes.byref(h)))
+        return UniversalSRS(self.ctx, self.curve_id, h, len(powers_limbs) - 1, powers_limbs)
+
+    # -- index -----------------------------------------------------------------------------------------
+    def index(self, srs, r1cs):
+        """[reference src/lib.rs:100-148] -> IndexProverKey (device resident); .vk_bytes is `index_vk` (ToBytes)."""
+        L = _lib.lib()
+        h = ctypes.c_void_p()
+        a, b, c = r1cs.matrices()
+        _lib.check(L.b2m_index_create(srs.handle, self.pc, r1cs.num_constraints, r1cs.num_variables, r1cs.num_instance,
+                                      ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(h)))
+        return IndexProverKey(srs, h, r1cs, self.pc)
+
+    # -- prove -----------------------------------------------------------------------------------------
+    def prove(self, index_pk, r1cs, zk_rng):
+        """[reference src/lib.rs:151-311] -> `CanonicalSerialize` bytes of `Proof<F, PC>`."""
+        L = _lib.lib()
+        buf = (ctypes.c_uint8 * 2048)()
+        n = ctypes.c_size_t(0)
+        inst = np.ascontiguousarray(r1cs.instance)
+        wit = np.ascontiguousarray(r1cs.witness)
+        _lib.check(L.b2m_prove(index_pk.handle, _lib.ptr(inst), len(inst), _lib.ptr(wit), len(wit), ctypes.byref(zk_rng.c), buf, 2048,
+                               ctypes.byref(n)))
+        return bytes(buf[:n.value])

@@ -1,6 +1,7 @@
 // extern "C" boundary of libb2m.so (declared in include/b2m.h).  Level 0: NTT / MSM / SRS.
 // The prover-level entry points live in prover.cu.
 #include "capi_types.cuh"
+#include "prover.cuh"
 
 namespace b2m {
 thread_local std::string g_last_error;
@@ -40,12 +41,12 @@ int b2m_ntt(b2m_ctx* ctx, int curve, uint64_t* data, unsigned log_n, int inverse
 }
 
 int b2m_srs_create(b2m_ctx* ctx, int curve, const uint64_t* powers_of_g, size_t n_g, const uint64_t* powers_of_gamma_g,
-                   size_t n_gamma, int window_bits, b2m_srs** out) {
+                   const uint64_t* gamma_indices, size_t n_gamma, int window_bits, b2m_srs** out) {
   return guard([&] {
     B2M_REQUIRE(ctx && powers_of_g && out, B2M_ERR_INVALID_ARG, "null argument");
     B2M_REQUIRE(curve == B2M_CURVE_BLS12_381 || curve == B2M_CURVE_BN254, B2M_ERR_INVALID_ARG, "unknown curve id");
     ctx->cx.use();
-    *out = new b2m_srs(ctx, curve, powers_of_g, n_g, powers_of_gamma_g, n_gamma, window_bits);
+    *out = new b2m_srs(ctx, curve, powers_of_g, n_g, powers_of_gamma_g, gamma_indices, n_gamma, window_bits);
   });
 }
 
@@ -75,7 +76,7 @@ int b2m_msm_g1(b2m_ctx* ctx, int curve, const uint64_t* bases_xy, const uint64_t
     if (out_is_inf) *out_is_inf = 1;
     return B2M_OK;
   }
-  int rc = b2m_srs_create(ctx, curve, bases_xy, n, nullptr, 0, 0, &srs);
+  int rc = b2m_srs_create(ctx, curve, bases_xy, n, nullptr, nullptr, 0, 0, &srs);
   if (rc != B2M_OK) return rc;
   rc = b2m_srs_msm(srs, 0, scalars, n, out_xy, out_is_inf);
   b2m_srs_destroy(srs);
@@ -89,6 +90,74 @@ int b2m_g1_powers(b2m_ctx* ctx, int curve, const uint64_t* g_xy, const uint64_t*
     if (curve == B2M_CURVE_BLS12_381) Msm<FrBls, FqBls>::g1_powers_host(ctx->cx, g_xy, beta, n, out_powers_xy);
     else if (curve == B2M_CURVE_BN254) Msm<FrBn, FqBn>::g1_powers_host(ctx->cx, g_xy, beta, n, out_powers_xy);
     else throw Error(B2M_ERR_INVALID_ARG, "unknown curve id");
+  });
+}
+
+// ---- Level 2 ----------------------------------------------------------------------------------
+struct b2m_index {
+  b2m_srs* srs;
+  std::unique_ptr<IndexBase> impl;
+};
+
+int b2m_index_create(b2m_srs* srs, int pc_variant, size_t num_constraints, size_t num_variables, size_t num_instance_variables,
+                     const b2m_matrix* a, const b2m_matrix* b, const b2m_matrix* c, b2m_index** out) {
+  return guard([&] {
+    B2M_REQUIRE(srs && a && b && c && out, B2M_ERR_INVALID_ARG, "null argument");
+    B2M_REQUIRE(pc_variant == B2M_PC_MARLIN_KZG10 || pc_variant == B2M_PC_SONIC_KZG10, B2M_ERR_INVALID_ARG, "unknown PC variant");
+    srs->ctx->cx.use();
+    std::unique_ptr<b2m_index> idx(new b2m_index);
+    idx->srs = srs;
+    if (srs->curve == B2M_CURVE_BLS12_381)
+      idx->impl.reset(make_index_bls(srs, pc_variant, num_constraints, num_variables, num_instance_variables, a, b, c));
+    else
+      idx->impl.reset(make_index_bn(srs, pc_variant, num_constraints, num_variables, num_instance_variables, a, b, c));
+    *out = idx.release();
+  });
+}
+
+void b2m_index_destroy(b2m_index* idx) {
+  if (!idx) return;
+  idx->srs->ctx->cx.use();
+  cudaStreamSynchronize(idx->srs->ctx->cx.stream);
+  delete idx;
+}
+
+int b2m_index_vk_bytes(const b2m_index* idx, uint8_t* out, size_t cap, size_t* len) {
+  return guard([&] {
+    B2M_REQUIRE(idx && len, B2M_ERR_INVALID_ARG, "null argument");
+    *len = idx->impl->vk_bytes.size();
+    if (out) {
+      B2M_REQUIRE(cap >= *len, B2M_ERR_INVALID_ARG, "buffer too small (%zu < %zu)", cap, *len);
+      memcpy(out, idx->impl->vk_bytes.data(), *len);
+    }
+  });
+}
+
+int b2m_index_comms(const b2m_index* idx, uint64_t* out_xy) {
+  return guard([&] {
+    B2M_REQUIRE(idx && out_xy, B2M_ERR_INVALID_ARG, "null argument");
+    memcpy(out_xy, idx->impl->comms_xy.data(), idx->impl->comms_xy.size() * sizeof(uint64_t));
+  });
+}
+
+int b2m_prove(b2m_index* idx, const uint64_t* formatted_input, size_t n_input, const uint64_t* witness, size_t n_witness,
+              b2m_rng* zk_rng, uint8_t* proof, size_t cap, size_t* proof_len) {
+  return guard([&] {
+    B2M_REQUIRE(idx && formatted_input && (witness || n_witness == 0) && proof && proof_len, B2M_ERR_INVALID_ARG, "null argument");
+    B2M_REQUIRE(zk_rng != nullptr, B2M_ERR_MISSING_RNG, "zk_rng is required (hiding commitments)");
+    idx->srs->ctx->cx.use();
+    std::vector<uint8_t> bytes;
+    idx->impl->prove(formatted_input, n_input, witness, n_witness, zk_rng, bytes);
+    *proof_len = bytes.size();
+    B2M_REQUIRE(cap >= bytes.size(), B2M_ERR_INVALID_ARG, "proof buffer too small (%zu < %zu)", cap, bytes.size());
+    memcpy(proof, bytes.data(), bytes.size());
+  });
+}
+
+int b2m_prove_timings(const b2m_index* idx, char* json, size_t cap) {
+  return guard([&] {
+    B2M_REQUIRE(idx && json && cap > 0, B2M_ERR_INVALID_ARG, "null argument");
+    snprintf(json, cap, "%s", idx->impl->timings_json.c_str());
   });
 }
 

@@ -46,12 +46,23 @@ struct b2m_srs {
   size_t n_g, n_gamma;
   std::unique_ptr<b2m::Msm<b2m::FrBls, b2m::FqBls>> bls;
   std::unique_ptr<b2m::Msm<b2m::FrBn, b2m::FqBn>> bn;
-  // powers_of_gamma_g (hiding bases), device resident, raw bytes (Affine<Fq>[n_gamma])
+  // powers_of_gamma_g (hiding bases), device resident, raw bytes (Affine<Fq>[n_gamma]);
+  // gamma_idx[k] = the power of beta held in slot k.
   void* gamma_dev = nullptr;
+  std::vector<uint64_t> gamma_idx;
 
-  b2m_srs(b2m_ctx* c, int curve_, const uint64_t* g, size_t ng, const uint64_t* gamma, size_t ngamma, int window_bits)
+  // slot of beta^i * gamma * G, or throws
+  size_t gamma_slot(uint64_t i) const {
+    for (size_t k = 0; k < gamma_idx.size(); k++)
+      if (gamma_idx[k] == i) return k;
+    throw b2m::Error(B2M_ERR_INVALID_ARG, b2m::fmt("the SRS holds no power %llu of gamma*G", (unsigned long long)i));
+  }
+
+  b2m_srs(b2m_ctx* c, int curve_, const uint64_t* g, size_t ng, const uint64_t* gamma, const uint64_t* gidx, size_t ngamma,
+          int window_bits)
       : ctx(c), curve(curve_), n_g(ng), n_gamma(ngamma) {
     using namespace b2m;
+    for (size_t k = 0; k < ngamma; k++) gamma_idx.push_back(gidx ? gidx[k] : k);
     if (curve == B2M_CURVE_BLS12_381) {
       bls.reset(new Msm<FrBls, FqBls>(c->cx, reinterpret_cast<const Affine<FqBls>*>(g), ng, window_bits));
       if (ngamma) {

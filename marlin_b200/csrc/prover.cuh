@@ -1,0 +1,27 @@
+// Curve-independent interface of the device-resident index / prover (Level 2 of include/b2m.h).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+struct b2m_srs;
+
+namespace b2m {
+
+struct IndexBase {
+  virtual ~IndexBase() {}
+  // `Marlin::prove` [reference src/lib.rs:151-311]
+  virtual void prove(const uint64_t* formatted_input, size_t n_input, const uint64_t* witness, size_t n_witness, b2m_rng* zk_rng,
+                     std::vector<uint8_t>& proof) = 0;
+  std::vector<uint8_t> vk_bytes;    // IndexVerifierKey::write (ToBytes)
+  std::vector<uint64_t> comms_xy;   // six index commitments, affine Montgomery limbs
+  std::string timings_json;
+};
+
+IndexBase* make_index_bls(b2m_srs* srs, int pc, size_t num_constraints, size_t num_variables, size_t num_instance,
+                          const b2m_matrix* a, const b2m_matrix* b, const b2m_matrix* c);
+IndexBase* make_index_bn(b2m_srs* srs, int pc, size_t num_constraints, size_t num_variables, size_t num_instance,
+                         const b2m_matrix* a, const b2m_matrix* b, const b2m_matrix* c);
+
+}  // namespace b2m

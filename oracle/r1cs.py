@@ -115,10 +115,10 @@ def dense_circuit(field, seed, num_constraints, num_variables, per_row):
     config 1's "dense" case; generator documented in DESIGN.md): z random, A and B rows random,
     C row = single fresh witness holding (A z)(B z)."""
     import random
-    rnd = random.Random(seed)
     p = field.p
 
     def gen(cs):
+        rnd = random.Random(seed)  # re-seeded per synthesis: index() and prove() must see the same system
         pub = cs.new_input_variable(rnd.randrange(p))
         free = [pub]
         vals = {pub: cs.instance[1]}

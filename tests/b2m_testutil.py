@@ -58,12 +58,13 @@ def gpu_powers(ctx, curve, g, beta, n):
     return out
 
 
-def make_srs(ctx, curve, powers_limbs, gamma_limbs=None, window_bits=0):
+def make_srs(ctx, curve, powers_limbs, gamma_limbs=None, gamma_indices=None, window_bits=0):
     L = _lib.lib()
     h = ctypes.c_void_p()
     ng = 0 if gamma_limbs is None else len(gamma_limbs)
+    gi = None if gamma_indices is None else np.asarray(gamma_indices, dtype=np.uint64)
     _lib.check(L.b2m_srs_create(ctx, CURVE_ID[curve.name], _lib.ptr(powers_limbs), len(powers_limbs),
-                                _lib.ptr(gamma_limbs), ng, window_bits, ctypes.byref(h)))
+                                _lib.ptr(gamma_limbs), _lib.ptr(gi), ng, window_bits, ctypes.byref(h)))
     return h
 
 

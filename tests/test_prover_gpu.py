@@ -1,0 +1,133 @@
+"""GPU parity of the Level-2 ABI (b2m_index_create / b2m_prove) against the oracle: the index
+verifier-key bytes and the serialized proof must be BYTE-IDENTICAL to the oracle's on the same SRS,
+instance and RNG streams, and the oracle's verifier must accept the GPU proof (and reject it for a
+wrong public input), mirroring reference src/test.rs:158-161."""
+import numpy as np
+import pytest
+
+import b2m_testutil as util
+from marlin_b200 import api, r1cs as gr1cs
+from oracle import kzg, marlin as omarlin, r1cs as or1cs
+from oracle import rng as orng
+from oracle.params import BLS12_381, BN254
+
+pytestmark = pytest.mark.gpu
+
+SCHEMES = {"marlin_kzg10": kzg.MARLIN, "sonic_kzg10": kzg.SONIC}
+
+
+def run_case(ctx, curve, scheme, ocirc, gcirc, public_input, zk_seed=bytes(range(32)), beta=0x1234567, window_bits=0):
+    f = curve.fr
+    cs = or1cs.synthesize(f, ocirc)
+    nnz = sum(len(set(i for _, i in ra) | set(i for _, i in rb) | set(i for _, i in rc)) for ra, rb, rc in zip(*cs.to_matrices()))
+    osrs = omarlin.universal_setup(curve, cs.num_constraints, len(cs.instance) + len(cs.witness), nnz, beta=beta, g_scalar=3, gamma=11)
+    eng = kzg.Engine(use_trapdoor=True)
+    opk = omarlin.index(osrs, ocirc, SCHEMES[scheme], eng)
+    zk = orng.ChaChaRng(zk_seed, 12)
+    oproof = omarlin.prove(opk, ocirc, zk, eng)
+    obytes = omarlin.serialize_proof(curve, SCHEMES[scheme], oproof)
+    assert omarlin.verify(opk, public_input, oproof)
+
+    m = api.Marlin(curve.name, scheme, ctx=ctx)
+    powers = util.points_to_limbs(curve, osrs.powers_of_g)
+    bounds = opk.ck.enforced_degree_bounds
+    gidx = [0, 1, 2]
+    if scheme == "sonic_kzg10":
+        for d in bounds:
+            gidx += [osrs.max_degree - d + i for i in range(3)]
+    gidx = sorted(set(gidx))
+    gam = util.points_to_limbs(curve, [osrs.power_of_gamma_g(i) for i in gidx])
+    srs = m.srs_from_points(powers, gam, gidx, window_bits)
+    try:
+        pk = m.index(srs, gcirc)
+        try:
+            assert pk.vk_bytes == opk.vk_bytes, "index_vk (ToBytes) differs"
+            grng = api.ZkRng(zk_seed, 12)
+            gbytes = m.prove(pk, gcirc, grng)
+            assert grng.word_pos == zk.word_pos, "zk_rng consumption differs"
+            assert gbytes == obytes, "proof bytes differ"
+            # a second proof continues the same RNG stream, like the reference's loop (test.rs:138-161)
+            oproof2 = omarlin.prove(opk, ocirc, zk, eng)
+            assert m.prove(pk, gcirc, grng) == omarlin.serialize_proof(curve, SCHEMES[scheme], oproof2)
+            assert not omarlin.verify(opk, [(x + 1) % f.p for x in public_input], oproof)
+            return pk.timings()
+        finally:
+            pk.close()
+    finally:
+        srs.close()
+
+
+@pytest.fixture(scope="module")
+def gctx(b2m_ctx):
+    c = api.Context.__new__(api.Context)
+    c.handle = b2m_ctx
+    return c
+
+
+# the reference's own shapes [reference src/test.rs:163-203]: (num_constraints, num_variables)
+REF_SHAPES = {"tall_big": (100, 25), "tall_small": (26, 25), "squat_big": (25, 100), "squat_small": (25, 26), "square": (25, 25)}
+
+
+@pytest.mark.parametrize("shape", list(REF_SHAPES))
+@pytest.mark.parametrize("scheme", list(SCHEMES))
+def test_reference_test_circuits(gctx, shape, scheme):
+    curve = BLS12_381
+    nc, nv = REF_SHAPES[shape]
+    rng = orng.test_rng()
+    a, b = orng.field_rand(curve.fr, rng), orng.field_rand(curve.fr, rng)
+    c = a * b % curve.fr.p
+    d = c * b % curve.fr.p
+    run_case(gctx, curve, scheme, or1cs.test_circuit(curve.fr, a, b, nc, nv), gr1cs.test_circuit(0, a, b, nc, nv), [c, d])
+
+
+@pytest.mark.parametrize("log_n", [4, 8, 10])
+@pytest.mark.parametrize("scheme", list(SCHEMES))
+def test_dummy_circuit(gctx, log_n, scheme):
+    """BASELINE.json config 1 (2^10, the reference bench's DummyCircuit shape) and smaller."""
+    curve = BLS12_381
+    n = 1 << log_n
+    rng = orng.test_rng()
+    a, b = orng.field_rand(curve.fr, rng), orng.field_rand(curve.fr, rng)
+    t = run_case(gctx, curve, scheme, or1cs.dummy_circuit(curve.fr, a, b, 10, n), gr1cs.dummy_circuit(0, a, b, 10, n), [a * b % curve.fr.p])
+    assert "Marlin::Prover" in t
+
+
+def test_dense_circuit(gctx):
+    """BASELINE.json config 1's "dense" case: seeded random R1CS, 8 non-zeros per row per matrix."""
+    curve = BLS12_381
+    gen = or1cs.dense_circuit(curve.fr, seed=42, num_constraints=48, num_variables=80, per_row=8)
+    cs = or1cs.synthesize(curve.fr, gen)
+    a, b, c = or1cs.ConstraintSystem.to_matrices(cs)
+    g = gr1cs.from_rows(0, a, b, c, cs.instance, cs.witness)
+    run_case(gctx, curve, "marlin_kzg10", gen, g, cs.instance[1:])
+
+
+@pytest.mark.parametrize("scheme", list(SCHEMES))
+def test_bn254(gctx, scheme):
+    """BASELINE.json config 4's curve (second field/curve instantiation) at a size the oracle proves in seconds."""
+    curve = BN254
+    rng = orng.test_rng()
+    a, b = orng.field_rand(curve.fr, rng), orng.field_rand(curve.fr, rng)
+    run_case(gctx, curve, scheme, or1cs.dummy_circuit(curve.fr, a, b, 10, 64), gr1cs.dummy_circuit(1, a, b, 10, 64), [a * b % curve.fr.p])
+
+
+def test_error_codes(gctx):
+    """Error behaviour mirrors the reference: IndexTooLarge, InstanceDoesNotMatchIndex."""
+    from marlin_b200 import _lib
+    curve = BLS12_381
+    m = api.Marlin("bls12_381", "marlin_kzg10", ctx=gctx)
+    srs = m.srs_from_trapdoor(63, beta=5)
+    try:
+        big = gr1cs.dummy_circuit(0, 3, 4, 10, 64)
+        with pytest.raises(_lib.B2MError) as e:
+            m.index(srs, big)
+        assert e.value.code == 2  # B2M_ERR_INDEX_TOO_LARGE
+        small = gr1cs.dummy_circuit(0, 3, 4, 10, 16)
+        pk = m.index(srs, small)
+        other = gr1cs.dummy_circuit(0, 3, 4, 10, 8)
+        with pytest.raises(_lib.B2MError) as e:
+            m.prove(pk, other, api.ZkRng())
+        assert e.value.code == 3  # B2M_ERR_INSTANCE_MISMATCH
+        pk.close()
+    finally:
+        srs.close()
