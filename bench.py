@@ -1,0 +1,234 @@
+#!/usr/bin/env python3
+"""bench.py -- Marlin prover throughput on B200 (BASELINE.json metric: prover constraints/sec, BLS12-381).
+
+A "step" is one `Marlin::prove` (reference src/lib.rs:151-311) of the reference bench's DummyCircuit
+(benches/bench.rs:25-67) scaled to 2^log_n constraints; SRS generation and `index` are outside the
+timed region exactly as in benches/bench.rs:79-101.
+
+  value : constraints / second with the instance (x, w) already resident in HBM (b2m_index_stage)
+  e2e   : the same through the public API with HOST buffers -- host->device copy of the instance and
+          device->host read of the proof inside the timed region
+  roofline     : the dominant kernel (msm_accumulate_kernel) -- algorithmic bytes (128 B per
+                 (base, scalar) pair) / CUDA-event kernel time / measured HBM peak
+  cpu_baseline : the oracle's C port of the reference's CPU algorithms timed on this box's host cores
+                 (rank 0, N = 1), on a bounded sample (a smaller instance of the same circuit family)
+
+N > 1 (torchrun, one rank per GPU): every rank runs the prover, each MSM is sharded by base/scalar
+chunk and the partial sums are exchanged with one NCCL all-gather per MSM (DESIGN.md "Multi-GPU");
+total work is fixed => "scaling": "strong".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-n", type=int, default=20, help="log2 of the number of constraints (BASELINE config 2: 20)")
+    ap.add_argument("--pc", default="marlin_kzg10", choices=["marlin_kzg10", "sonic_kzg10"])
+    ap.add_argument("--curve", default="bls12_381", choices=["bls12_381", "bn254"])
+    ap.add_argument("--cpu-log-n", type=int, default=14, help="instance size of the bounded CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop = threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append((float(out[0]), float(out[1])))
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=3)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(args):
+    """Oracle C port (oracle/cport) of the reference's CPU algorithms on this box's host cores."""
+    try:
+        from oracle import cport
+        return cport.prover_baseline(args.curve, args.pc, args.cpu_log_n)
+    except Exception as e:  # the baseline is reported, never required for the GPU number
+        return {"value": None, "unit": "constraints/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 3))):
+        base = cpu_baseline(args)
+        if base.get("value"):
+            vals.append(base["value"])
+    v = sum(vals) / len(vals) if vals else None
+    n = 1 << args.cpu_log_n
+    line = {
+        "impl": "reference", "metric": "prover_constraints_per_sec", "value": v, "unit": "constraints/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": (1000.0 * n / v) if v else None, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32-limb modular integers (Fr 255-bit, Fq 381-bit)", "data": "synthetic",
+        "config": {"workload": f"Marlin::prove, DummyCircuit 2^{args.log_n} constraints, {args.curve}, {args.pc}",
+                   "sampled_on": f"2^{args.cpu_log_n} constraints (bounded CPU sample of the same circuit family)"},
+        "cpu_baseline": dict(base or {}, value=v),
+        "e2e": {"value": v, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from marlin_b200 import api, r1cs
+    n = 1 << args.log_n
+    m = api.Marlin(args.curve, args.pc, device=local_rank)
+    if world > 1:
+        from marlin_b200 import multi
+        multi.attach(m.ctx, dist, rank, world)
+    cid = m.curve_id
+    a, b = 0x1234567890abcdef1234567890abcdef, 0xfedcba0987654321fedcba0987654321
+    circ = r1cs.dummy_circuit(cid, a, b, 10, n)
+    t0 = time.time()
+    srs = m.universal_setup(n, n, 3 * n, beta=0x5eed5eed5eed5eed5eed5eed, gamma=7, degree_bounds=(n - 2, 4 * n - 2))
+    pk = m.index(srs, circ)
+    setup_s = time.time() - t0
+    m.stage(pk, circ)
+    zk = api.ZkRng()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        m.prove(pk, None, zk)
+    barrier()
+    # ---- timed region 1: device-resident inputs (value), per-kernel events on ---------------------
+    launches0 = m.ctx.launches()
+    m.ctx.profile(True)
+    dev_ms = []
+    with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            m.prove(pk, None, zk)
+            dev_ms.append(pk.timings()["Marlin::Prover"])  # CUDA events on the library's stream
+        barrier()
+        wall = time.perf_counter() - t0
+    kern = m.ctx.profile_report()
+    m.ctx.profile(False)
+    launches = m.ctx.launches() - launches0
+    phases = pk.timings()
+    # ---- timed region 2: end to end through the public API with host buffers ------------------------
+    barrier()
+    t0 = time.perf_counter()
+    proof = b""
+    for _ in range(args.steps):
+        proof = m.prove(pk, circ, zk)
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+
+    ms_step = sum(dev_ms) / len(dev_ms)
+    if dist is not None:  # max over ranks
+        t = torch.tensor([ms_step, wall, wall_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, wall, wall_e2e = (float(x) for x in t.tolist())
+    value = n / (ms_step / 1e3)
+    e2e_value = n * args.steps / wall_e2e
+    peaks, peak_kind = measured_peaks()
+    acc = kern.get("msm_accumulate_kernel", {"ms": 0.0, "units": 0.0, "launches": 0})
+    pair_bytes = 128 if args.curve == "bls12_381" else 96
+    achieved = (acc["units"] * pair_bytes / (acc["ms"] / 1e3) / 1e9) if acc["ms"] else None
+    line = {
+        "metric": "prover_constraints_per_sec", "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32-limb modular integers (Fr 255-bit, Fq 381-bit)", "data": "synthetic",
+        "config": {"workload": f"Marlin::prove, DummyCircuit 2^{args.log_n} constraints (|H|=2^{args.log_n}, |K|=2^{args.log_n + 2}), "
+                               f"{args.curve}, {args.pc}, SimpleHashFiatShamirRng<Blake2s,ChaChaRng>",
+                   "timing": "CUDA events on the library stream around each prove; working set (SRS tables + index + polynomials, "
+                             "> 7 GB) exceeds L2, no flush needed",
+                   "msm_window_bits": None, "parallelism": f"msm-shard x{world}" if world > 1 else "single"},
+        "wall_ms_per_step": 1e3 * wall / args.steps,
+        "gpu_launches": launches // args.steps,
+        "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": int(circ.instance.nbytes + circ.witness.nbytes),
+                "d2h_bytes_per_step": len(proof) + 15 * 96},
+        "clocks": clocks.summary(),
+        "roofline": {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                     "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None, "peak_source": peak_kind,
+                     "algorithmic_bytes_per_pair": pair_bytes,
+                     "note": "integer-ALU bound (profiles/r01_microbench_int_alu.json); see DESIGN.md Rooflines"},
+        "kernels": kern, "phases_ms": phases, "setup_s": setup_s, "proof_bytes": len(proof),
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line))
+    pk.close()
+    srs.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -60,6 +60,11 @@ int b2m_ctx_create(int device, b2m_ctx** out);
 void b2m_ctx_destroy(b2m_ctx* ctx);
 /* Number of kernel launches issued through this context so far. */
 unsigned long long b2m_ctx_launches(const b2m_ctx* ctx);
+/* Per-kernel device timing (CUDA events on the context's stream) for the dominant kernels: enable,
+ * run, then read {"kernel": {"launches", "ms", "units"}} -- units are (base, scalar) pairs for the MSM
+ * kernels and points for the NTT.  Reading the report clears it. */
+int b2m_ctx_profile(b2m_ctx* ctx, int enable);
+int b2m_ctx_profile_report(b2m_ctx* ctx, char* json, size_t cap);
 
 /* ---- Level 0: kernel ABI ------------------------------------------------------------- */
 
@@ -139,6 +144,11 @@ typedef struct {
 int b2m_prove(b2m_index* idx, const uint64_t* formatted_input, size_t n_input,
               const uint64_t* witness, size_t n_witness, b2m_rng* zk_rng, uint8_t* proof,
               size_t cap, size_t* proof_len);
+
+/* Copy an instance into HBM ahead of time.  A later b2m_prove(idx, NULL, 0, NULL, 0, ...) proves the
+ * staged instance without any host-to-device input traffic (bench.py's device-resident timing). */
+int b2m_index_stage(b2m_index* idx, const uint64_t* formatted_input, size_t n_input,
+                    const uint64_t* witness, size_t n_witness);
 
 /* Per-phase device timings of the last b2m_prove on this index (milliseconds), labelled
  * with the reference's own timer names (ark_std start_timer! labels). */

@@ -53,6 +53,8 @@ def lib():
         L.b2m_ctx_destroy.restype = None
         L.b2m_ctx_launches.argtypes = [vp]
         L.b2m_ctx_launches.restype = ctypes.c_ulonglong
+        L.b2m_ctx_profile.argtypes = [vp, ci]
+        L.b2m_ctx_profile_report.argtypes = [vp, ctypes.c_char_p, sz]
         L.b2m_ntt.argtypes = [vp, ci, vp, ctypes.c_uint, ci, ci]
         L.b2m_msm_g1.argtypes = [vp, ci, vp, vp, sz, vp, P(ci)]
         L.b2m_srs_create.argtypes = [vp, ci, vp, sz, vp, vp, sz, ci, P(vp)]
@@ -69,6 +71,7 @@ def lib():
             L.b2m_index_destroy.restype = None
             L.b2m_index_vk_bytes.argtypes = [vp, vp, sz, P(sz)]
             L.b2m_index_comms.argtypes = [vp, vp]
+            L.b2m_index_stage.argtypes = [vp, vp, sz, vp, sz]
             L.b2m_prove.argtypes = [vp, vp, sz, vp, sz, P(Rng), vp, sz, P(sz)]
             L.b2m_prove_timings.argtypes = [vp, ctypes.c_char_p, sz]
         _lib = L

@@ -30,6 +30,23 @@ void b2m_ctx_destroy(b2m_ctx* ctx) {
 
 unsigned long long b2m_ctx_launches(const b2m_ctx* ctx) { return ctx ? ctx->cx.launches : 0; }
 
+int b2m_ctx_profile(b2m_ctx* ctx, int enable) {
+  return guard([&] {
+    B2M_REQUIRE(ctx != nullptr, B2M_ERR_INVALID_ARG, "null argument");
+    ctx->cx.use();
+    if (!enable) ctx->cx.span_report();
+    ctx->cx.profiling = enable != 0;
+  });
+}
+
+int b2m_ctx_profile_report(b2m_ctx* ctx, char* json, size_t cap) {
+  return guard([&] {
+    B2M_REQUIRE(ctx && json && cap > 0, B2M_ERR_INVALID_ARG, "null argument");
+    ctx->cx.use();
+    snprintf(json, cap, "%s", ctx->cx.span_report().c_str());
+  });
+}
+
 int b2m_ntt(b2m_ctx* ctx, int curve, uint64_t* data, unsigned log_n, int inverse, int coset) {
   return guard([&] {
     B2M_REQUIRE(ctx && data, B2M_ERR_INVALID_ARG, "null argument");
@@ -143,7 +160,8 @@ int b2m_index_comms(const b2m_index* idx, uint64_t* out_xy) {
 int b2m_prove(b2m_index* idx, const uint64_t* formatted_input, size_t n_input, const uint64_t* witness, size_t n_witness,
               b2m_rng* zk_rng, uint8_t* proof, size_t cap, size_t* proof_len) {
   return guard([&] {
-    B2M_REQUIRE(idx && formatted_input && (witness || n_witness == 0) && proof && proof_len, B2M_ERR_INVALID_ARG, "null argument");
+    B2M_REQUIRE(idx && proof && proof_len, B2M_ERR_INVALID_ARG, "null argument");
+    B2M_REQUIRE(formatted_input == nullptr || witness || n_witness == 0, B2M_ERR_INVALID_ARG, "null witness");
     B2M_REQUIRE(zk_rng != nullptr, B2M_ERR_MISSING_RNG, "zk_rng is required (hiding commitments)");
     idx->srs->ctx->cx.use();
     std::vector<uint8_t> bytes;
@@ -151,6 +169,14 @@ int b2m_prove(b2m_index* idx, const uint64_t* formatted_input, size_t n_input, c
     *proof_len = bytes.size();
     B2M_REQUIRE(cap >= bytes.size(), B2M_ERR_INVALID_ARG, "proof buffer too small (%zu < %zu)", cap, bytes.size());
     memcpy(proof, bytes.data(), bytes.size());
+  });
+}
+
+int b2m_index_stage(b2m_index* idx, const uint64_t* formatted_input, size_t n_input, const uint64_t* witness, size_t n_witness) {
+  return guard([&] {
+    B2M_REQUIRE(idx && formatted_input && (witness || n_witness == 0), B2M_ERR_INVALID_ARG, "null argument");
+    idx->srs->ctx->cx.use();
+    idx->impl->stage(formatted_input, n_input, witness, n_witness);
   });
 }
 

@@ -49,6 +49,49 @@ struct Ctx {
   cudaMemPool_t pool = nullptr;
   // kernel-launch counter (bench.py reports it as gpu_launches)
   unsigned long long launches = 0;
+  // optional per-kernel timing (CUDA events on `stream`) for the roofline line of bench.py
+  struct Span {
+    std::string name;
+    double units;
+    cudaEvent_t a, b;
+  };
+  bool profiling = false;
+  std::vector<Span> spans;
+  size_t span_begin(const char* name, double units) {
+    if (!profiling) return (size_t)-1;
+    Span s{name, units, nullptr, nullptr};
+    cudaEventCreate(&s.a);
+    cudaEventCreate(&s.b);
+    cudaEventRecord(s.a, stream);
+    spans.push_back(s);
+    return spans.size() - 1;
+  }
+  void span_end(size_t id) {
+    if (id != (size_t)-1) cudaEventRecord(spans[id].b, stream);
+  }
+  // {"name": {"launches": n, "ms": total, "units": total}, ...}; clears the log
+  std::string span_report() {
+    cudaStreamSynchronize(stream);
+    struct Acc { double ms = 0, units = 0; long n = 0; };
+    std::vector<std::pair<std::string, Acc>> acc;
+    for (auto& s : spans) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, s.a, s.b);
+      cudaEventDestroy(s.a);
+      cudaEventDestroy(s.b);
+      size_t k = 0;
+      for (; k < acc.size(); k++)
+        if (acc[k].first == s.name) break;
+      if (k == acc.size()) acc.push_back({s.name, Acc()});
+      acc[k].second.ms += ms; acc[k].second.units += s.units; acc[k].second.n++;
+    }
+    spans.clear();
+    std::string out = "{";
+    for (size_t k = 0; k < acc.size(); k++)
+      out += fmt("%s\"%s\": {\"launches\": %ld, \"ms\": %.4f, \"units\": %.0f}", k ? ", " : "", acc[k].first.c_str(), acc[k].second.n,
+                 acc[k].second.ms, acc[k].second.units);
+    return out + "}";
+  }
 
   explicit Ctx(int dev) : device(dev) {
     B2M_CUDA(cudaSetDevice(dev));

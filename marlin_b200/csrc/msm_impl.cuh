@@ -288,6 +288,7 @@ void Msm<Fr, Fq>::run(const Fr* scalars, bool mont, size_t n, size_t base_off, c
   const uint32_t B = 1u << (c - 1);
   DBuf<uint32_t> digits(cx, (size_t)W * n), hist(cx, B), offsets(cx, B), cursor(cx, B), sorted(cx, (size_t)W * n);
   hist.zero();
+  size_t sp0 = cx.span_begin("msm_sort", (double)n);
   msm_digits_kernel<Fr><<<div_up(n, 256), 256, 0, cx.stream>>>(scalars, mont, n, c, W, digits.p, hist.p);
   B2M_CHECK_LAUNCH();
   cx.launches++;
@@ -296,11 +297,15 @@ void Msm<Fr, Fq>::run(const Fr* scalars, bool mont, size_t n, size_t base_off, c
   msm_scatter_kernel<<<div_up(n, 256), 256, 0, cx.stream>>>(digits.p, n, W, cursor.p, sorted.p);
   B2M_CHECK_LAUNCH();
   cx.launches++;
+  cx.span_end(sp0);
   DBuf<XYZZ<Fq>> buckets(cx, B);
+  size_t sp = cx.span_begin("msm_accumulate_kernel", (double)n);
   msm_accumulate_kernel<Fq><<<div_up(B, 128), 128, 0, cx.stream>>>(tables.p, n_srs, base_off, offsets.p, cursor.p, sorted.p, B,
                                                                     buckets.p);
   B2M_CHECK_LAUNCH();
   cx.launches++;
+  cx.span_end(sp);
+  size_t sp2 = cx.span_begin("msm_reduce", (double)n);
 
   // hierarchical reduction: W0(A) = L * W0(S) + sum T0, level by level
   std::vector<DBuf<XYZZ<Fq>>> keep;
@@ -326,6 +331,7 @@ void Msm<Fr, Fq>::run(const Fr* scalars, bool mont, size_t n, size_t base_off, c
   msm_finish_kernel<Fq><<<1, 256, 0, cx.stream>>>(levels, cur, extra, n_extra, out_xyzz, out_affine);
   B2M_CHECK_LAUNCH();
   cx.launches++;
+  cx.span_end(sp2);
   // the DBufs are stream-ordered: their frees are enqueued behind the kernels above
 }
 

@@ -145,6 +145,7 @@ void Ntt<Fr>::run(Fr* work, Fr* out, int log_n, bool inverse) {
   int base = log_n / passes, extra = log_n % passes;
   Fr n_inv = Fr::from_u64((uint64_t)1 << log_n).inverse();
   int s0 = 0;
+  size_t sp = ctx->span_begin("ntt", (double)((size_t)1 << log_n));
   for (int p = 0; p < passes; p++) {
     int k = base + (p < extra ? 1 : 0);
     bool last = (p == passes - 1);
@@ -163,6 +164,7 @@ void Ntt<Fr>::run(Fr* work, Fr* out, int log_n, bool inverse) {
     ctx->launches++;
     s0 += k;
   }
+  ctx->span_end(sp);
 }
 
 template <class Fr>

@@ -14,6 +14,8 @@ struct IndexBase {
   // `Marlin::prove` [reference src/lib.rs:151-311]
   virtual void prove(const uint64_t* formatted_input, size_t n_input, const uint64_t* witness, size_t n_witness, b2m_rng* zk_rng,
                      std::vector<uint8_t>& proof) = 0;
+  // Copy an instance (x, w) into HBM ahead of time; a later prove() with null pointers uses it.
+  virtual void stage(const uint64_t* formatted_input, size_t n_input, const uint64_t* witness, size_t n_witness) = 0;
   std::vector<uint8_t> vk_bytes;    // IndexVerifierKey::write (ToBytes)
   std::vector<uint64_t> comms_xy;   // six index commitments, affine Montgomery limbs
   std::string timings_json;

@@ -437,8 +437,33 @@ struct MarlinIndex : IndexBase {
   // ---------------------------------------------------------------------------------------------
   // `Marlin::prove`
   // ---------------------------------------------------------------------------------------------
+  DBuf<Fr> staged_z;
+  std::vector<uint64_t> staged_input;
+
+  void check_instance(size_t n_input, size_t n_witness) const {
+    B2M_REQUIRE(n_input + n_witness == nv, B2M_ERR_INSTANCE_MISMATCH, "instance (%zu + %zu variables) does not match the index (%zu)",
+                n_input, n_witness, nv);
+    B2M_REQUIRE(n_input == ni && is_pow2(n_input), B2M_ERR_INVALID_PUBLIC_INPUT_LEN, "formatted public input length %zu (index: %zu)",
+                n_input, ni);
+  }
+  void stage(const uint64_t* formatted_input, size_t n_input, const uint64_t* witness, size_t n_witness) override {
+    check_instance(n_input, n_witness);
+    staged_z = DBuf<Fr>(cx, nv);
+    staged_z.upload(reinterpret_cast<const Fr*>(formatted_input), ni);
+    if (n_witness) B2M_CUDA(cudaMemcpyAsync(staged_z.p + ni, witness, n_witness * sizeof(Fr), cudaMemcpyHostToDevice, cx.stream));
+    staged_input.assign(formatted_input, formatted_input + 4 * ni);
+    cx.sync();
+  }
+
   void prove(const uint64_t* formatted_input, size_t n_input, const uint64_t* witness, size_t n_witness, b2m_rng* rng,
              std::vector<uint8_t>& proof) override {
+    const bool use_staged = formatted_input == nullptr;
+    if (use_staged) {
+      B2M_REQUIRE(staged_z.p != nullptr, B2M_ERR_INVALID_ARG, "no staged instance: call b2m_index_stage first");
+      formatted_input = staged_input.data();
+      n_input = ni;
+      n_witness = nv - ni;
+    }
     B2M_REQUIRE(n_input + n_witness == nv, B2M_ERR_INSTANCE_MISMATCH, "instance (%zu + %zu variables) does not match the index (%zu)",
                 n_input, n_witness, nv);
     B2M_REQUIRE(n_input == ni && is_pow2(n_input), B2M_ERR_INVALID_PUBLIC_INPUT_LEN, "formatted public input length %zu (index: %zu)",
@@ -456,8 +481,12 @@ struct MarlinIndex : IndexBase {
     // ---- prover_init [reference prover.rs:211-306] --------------------------------------------------
     size_t t_init = tm.begin("AHP::Prover::Init");
     DBuf<Fr> z(cx, nv), z_a(cx, H), z_b(cx, H);
-    z.upload(reinterpret_cast<const Fr*>(formatted_input), ni);
-    if (n_witness) B2M_CUDA(cudaMemcpyAsync(z.p + ni, witness, n_witness * sizeof(Fr), cudaMemcpyHostToDevice, cx.stream));
+    if (use_staged) {
+      B2M_CUDA(cudaMemcpyAsync(z.p, staged_z.p, nv * sizeof(Fr), cudaMemcpyDeviceToDevice, cx.stream));
+    } else {
+      z.upload(reinterpret_cast<const Fr*>(formatted_input), ni);
+      if (n_witness) B2M_CUDA(cudaMemcpyAsync(z.p + ni, witness, n_witness * sizeof(Fr), cudaMemcpyHostToDevice, cx.stream));
+    }
     z_a.zero(); z_b.zero();
     spmv_kernel<Fr><<<div_up(nc, 256), 256, 0, cx.stream>>>(a_rowptr.p, a_col.p, a_coeff.p, z.p, nc, z_a.p);
     spmv_kernel<Fr><<<div_up(nc, 256), 256, 0, cx.stream>>>(b_rowptr.p, b_col.p, b_coeff.p, z.p, nc, z_b.p);
