@@ -52,44 +52,61 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md): one
+    long-running `nvidia-smi -lms` process started before the warm-up (so its start-up cost never lands
+    in a timed step); mark() brackets the timed region and only samples inside it are summarised."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index = index
-        self.samples = []
-        self.reasons = set()
-        self.stop = threading.Event()
-        self.t = threading.Thread(target=self.run, daemon=True)
+    def __init__(self, index, period_ms=250):
+        self.lines = []
+        self.t_lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        self.t0 = self.t1 = None
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop.is_set():
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+            self.t_lines.append(time.time())
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
+    def close(self):
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append((float(out[0]), float(out[1])))
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                self.proc.wait(timeout=3)
             except Exception:
-                pass
-            self.stop.wait(0.2)
-
-    def __enter__(self):
-        self.t.start()
-        return self
-
-    def __exit__(self, *a):
-        self.stop.set()
-        self.t.join(timeout=3)
+                self.proc.kill()
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
-        sm = sorted(s[0] for s in self.samples)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons)}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm, mx, reasons = [], None, set()
+        for t, line in zip(self.t_lines, self.lines):
+            if self.t0 is None or self.t1 is None or not (self.t0 <= t <= self.t1 + 0.3):
+                continue
+            parts = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(parts[1]))
+                mx = float(parts[2])
+            except Exception:
+                continue
+            for n, v in zip(names, parts[3:]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def cpu_baseline(args):
@@ -162,6 +179,7 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    clocks = ClockSampler(local_rank)
     for _ in range(max(args.warmup, 3)):
         m.prove(pk, None, zk)
     barrier()
@@ -169,13 +187,14 @@ def main():
     launches0 = m.ctx.launches()
     m.ctx.profile(True)
     dev_ms = []
-    with ClockSampler(local_rank) as clocks:
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            m.prove(pk, None, zk)
-            dev_ms.append(pk.timings()["Marlin::Prover"])  # CUDA events on the library's stream
-        barrier()
-        wall = time.perf_counter() - t0
+    clocks.begin()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.prove(pk, None, zk)
+        dev_ms.append(pk.timings()["Marlin::Prover"])  # CUDA events on the library's stream
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks.end()
     kern = m.ctx.profile_report()
     m.ctx.profile(False)
     launches = m.ctx.launches() - launches0
@@ -188,6 +207,7 @@ def main():
         proof = m.prove(pk, circ, zk)
     barrier()
     wall_e2e = time.perf_counter() - t0
+    clocks.close()
 
     ms_step = sum(dev_ms) / len(dev_ms)
     if dist is not None:  # max over ranks
@@ -218,7 +238,7 @@ def main():
                      "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None, "peak_source": peak_kind,
                      "algorithmic_bytes_per_pair": pair_bytes,
                      "note": "integer-ALU bound (profiles/r01_microbench_int_alu.json); see DESIGN.md Rooflines"},
-        "kernels": kern, "phases_ms": phases, "setup_s": setup_s, "proof_bytes": len(proof),
+        "kernels": kern, "phases_ms": phases, "dev_ms_steps": dev_ms, "setup_s": setup_s, "proof_bytes": len(proof),
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

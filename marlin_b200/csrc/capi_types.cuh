@@ -64,13 +64,15 @@ struct b2m_srs {
     using namespace b2m;
     for (size_t k = 0; k < ngamma; k++) gamma_idx.push_back(gidx ? gidx[k] : k);
     if (curve == B2M_CURVE_BLS12_381) {
-      bls.reset(new Msm<FrBls, FqBls>(c->cx, reinterpret_cast<const Affine<FqBls>*>(g), ng, window_bits));
+      bls.reset(new Msm<FrBls, FqBls>(c->cx, reinterpret_cast<const Affine<FqBls>*>(g), ng, reinterpret_cast<const Affine<FqBls>*>(gamma), ngamma,
+                                      window_bits));
       if (ngamma) {
         gamma_dev = c->cx.alloc_bytes(ngamma * sizeof(Affine<FqBls>));
         B2M_CUDA(cudaMemcpyAsync(gamma_dev, gamma, ngamma * sizeof(Affine<FqBls>), cudaMemcpyHostToDevice, c->cx.stream));
       }
     } else {
-      bn.reset(new Msm<FrBn, FqBn>(c->cx, reinterpret_cast<const Affine<FqBn>*>(g), ng, window_bits));
+      bn.reset(new Msm<FrBn, FqBn>(c->cx, reinterpret_cast<const Affine<FqBn>*>(g), ng, reinterpret_cast<const Affine<FqBn>*>(gamma), ngamma,
+                                  window_bits));
       if (ngamma) {
         gamma_dev = c->cx.alloc_bytes(ngamma * sizeof(Affine<FqBn>));
         B2M_CUDA(cudaMemcpyAsync(gamma_dev, gamma, ngamma * sizeof(Affine<FqBn>), cudaMemcpyHostToDevice, c->cx.stream));

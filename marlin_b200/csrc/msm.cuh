@@ -25,36 +25,43 @@ namespace b2m {
 
 constexpr int MSM_MIN_WINDOW = 8;  // 5 window-id bits in a reference: ceil(256 / c) <= 32
 constexpr int MSM_IDX_BITS = 26;  // point index bits in a sorted reference
-constexpr int MSM_SEG = 16;       // segment length of the bucket reduction
-constexpr int MSM_RED_THREADS = 128;
 constexpr uint32_t MSM_NO_DIGIT = 0xffffffffu;
 
-struct MsmLevel {
-  const void* partials;  // XYZZ[count]: per-block T0 sums of this level
-  uint32_t count;
-  uint32_t log_l;        // log2 of this level's segment length
-};
-constexpr int MSM_MAX_LEVELS = 8;
-struct MsmLevels {
-  MsmLevel lv[MSM_MAX_LEVELS];
-  int n;
+template <class Fr, class Fq>
+struct MsmJob {
+  const Fr* scalars;       // device array
+  bool mont;               // Montgomery form (polynomial coefficients) or canonical integers
+  size_t n;
+  size_t base_off;         // slice powers_of_g[base_off .. base_off + n)
+  const Fr* scalars2;      // second scalar group (blinding coefficients) against the extra bases, or null
+  size_t n2;
+  size_t extra_base;       // first extra base (slot among the powers_of_gamma_g) used by scalars2
+  const XYZZ<Fq>* extra;   // further device-resident terms added to the result
+  int n_extra;
+  XYZZ<Fq>* out_xyzz;      // either output may be null
+  Affine<Fq>* out_affine;
 };
 
 template <class Fr, class Fq>
 struct Msm {
   Ctx* ctx;
-  size_t n_srs = 0;
+  size_t n_srs = 0;    // number of G1 powers
+  size_t n_extra = 0;  // further fixed bases (powers_of_gamma_g) appended after them
+  size_t stride = 0;   // n_srs + n_extra: entries per window table
   int c = 0, W = 0;
-  DBuf<Affine<Fq>> tables;  // [W][n_srs]:  tables[w * n_srs + i] = 2^(c*w) * P_i
+  DBuf<Affine<Fq>> tables;  // [W][stride]:  tables[w * stride + i] = 2^(c*w) * P_i
 
   static int pick_window(size_t n);
   // Upload the powers and build the window tables (key-load time).
-  Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, int window_bits);
+  Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, const Affine<Fq>* host_extra, size_t n_extra_bases, int window_bits);
 
   // sum_i scalars[i] * powers[base_off + i] (+ the `extra` XYZZ terms) -> out_xyzz / out_affine on
   // the device.  `scalars` is a device array, Montgomery form if mont, canonical otherwise.
   void run(const Fr* scalars, bool mont, size_t n, size_t base_off, const XYZZ<Fq>* extra, int n_extra, XYZZ<Fq>* out_xyzz,
            Affine<Fq>* out_affine);
+  // Several MSMs at once (the commitments of one prover round): bucket passes back to back, then ONE
+  // batched log-depth reduction, so its latency is paid per round instead of per MSM.
+  void run_batch(const MsmJob<Fr, Fq>* jobs, int nj);
   // sum_i scalars[i] * bases[i] for a handful of terms (n <= 4096): hiding commitments.
   void run_small(const Affine<Fq>* bases, const Fr* scalars, bool mont, int n, XYZZ<Fq>* out_xyzz);
   // Level-0 ABI bodies (include/b2m.h): host scalars in, host affine point out.

@@ -61,12 +61,15 @@ __global__ void msm_precompute_kernel(Affine<Fq>* tables, size_t n, int c, int W
 }
 
 // ---- 1. digits ----------------------------------------------------------------------------
-// digits[w * n + i] = (|d| - 1) | sign << 31, or MSM_NO_DIGIT for d == 0; hist[|d| - 1]++.
+// digits[w * nt + i] = (|d| - 1) | sign << 31, or MSM_NO_DIGIT for d == 0; hist[|d| - 1]++.
+// Scalars come in two groups: i < n from `scalars` (the polynomial), the rest from `scalars2`
+// (the few blinding coefficients that multiply the gamma powers), nt = n + n2.
 template <class Fr>
-__global__ void msm_digits_kernel(const Fr* scalars, bool MONT, size_t n, int c, int W, uint32_t* digits, uint32_t* hist) {
+__global__ void msm_digits_kernel(const Fr* scalars, const Fr* scalars2, bool MONT, size_t n, size_t nt, int c, int W, uint32_t* digits,
+                                  uint32_t* hist) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fr s = ld_fr(scalars + i);
+  if (i >= nt) return;
+  Fr s = i < n ? ld_fr(scalars + i) : ld_fr(scalars2 + (i - n));
   if (MONT) s = s.to_canonical();
   const uint32_t half = 1u << (c - 1);
   uint32_t carry = 0;
@@ -89,7 +92,7 @@ __global__ void msm_digits_kernel(const Fr* scalars, bool MONT, size_t n, int c,
       carry = 0;
       out = v ? (v - 1) : MSM_NO_DIGIT;
     }
-    digits[(size_t)w * n + i] = out;
+    digits[(size_t)w * nt + i] = out;
     if (out != MSM_NO_DIGIT) atomicAdd(hist + (out & 0x7fffffffu), 1u);
   }
 }
@@ -97,116 +100,204 @@ __global__ void msm_digits_kernel(const Fr* scalars, bool MONT, size_t n, int c,
 // ---- 2. exclusive scan of u32: scan.cuh -------------------------------------------------------
 
 // ---- 3. scatter -------------------------------------------------------------------------------
-// sorted[cursor[bucket]++] = i | w << 26 | sign << 31
-static __global__ void msm_scatter_kernel(const uint32_t* digits, size_t n, int W, uint32_t* cursor, uint32_t* sorted) {
+// Counting sort by bucket: sorted[pos] = {(absolute table index) | w << 26 | sign << 31, bucket}.
+static __global__ void msm_scatter_kernel(const uint32_t* digits, size_t n, size_t nt, size_t base_off, size_t idx2, int W,
+                                          uint32_t* cursor, uint2* sorted) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= nt) return;
+  uint32_t abs_idx = (uint32_t)(i < n ? base_off + i : idx2 + (i - n));
   for (int w = 0; w < W; w++) {
-    uint32_t d = digits[(size_t)w * n + i];
+    uint32_t d = digits[(size_t)w * nt + i];
     if (d == MSM_NO_DIGIT) continue;
-    uint32_t pos = atomicAdd(cursor + (d & 0x7fffffffu), 1u);
-    sorted[pos] = (uint32_t)i | ((uint32_t)w << MSM_IDX_BITS) | (d & 0x80000000u);
+    uint32_t bkt = d & 0x7fffffffu;
+    uint32_t pos = atomicAdd(cursor + bkt, 1u);
+    sorted[pos] = make_uint2(abs_idx | ((uint32_t)w << MSM_IDX_BITS) | (d & 0x80000000u), bkt);  // one 8-byte scattered store
   }
 }
 
 // ---- 4. accumulate ----------------------------------------------------------------------------
-// buckets[b] = sum of the referenced table points; one thread per bucket.  `ends` is the scatter
-// cursor after step 3 (cursor[b] == end of bucket b).  The next point is prefetched while the
+// Balanced bucket accumulation: the references are sorted by bucket, and every thread owns the same
+// number (MSM_Q) of consecutive references, so all lanes of a warp run the same number of XYZZ mixed
+// additions whatever the bucket-size distribution.  A run of references that covers a whole bucket
+// is stored straight into buckets[b]; the (at most two) runs per thread that cut a bucket are stored
+// as partials and stitched together by msm_stitch_kernel.  The next point is prefetched while the
 // current one is being added.
+constexpr int MSM_Q = 64;
+template <class Fq>
+struct MsmPartial {
+  XYZZ<Fq> pt;
+};
 template <class Fq>
 __global__ void __launch_bounds__(128)
-msm_accumulate_kernel(const Affine<Fq>* __restrict__ tables, size_t table_stride, size_t base_off,
-                      const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ends,
-                      const uint32_t* __restrict__ sorted, uint32_t num_buckets, XYZZ<Fq>* __restrict__ buckets) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= num_buckets) return;
-  uint32_t start = offsets[b];
-  uint32_t end = ends[b];
-  XYZZ<Fq> acc = XYZZ<Fq>::inf();
-  if (start < end) {
-    uint32_t ref = sorted[start];
-    Affine<Fq> p = ld_affine(tables + (size_t)((ref >> MSM_IDX_BITS) & 31u) * table_stride + base_off + (ref & ((1u << MSM_IDX_BITS) - 1)));
+msm_accumulate_kernel(const Affine<Fq>* __restrict__ tables, size_t table_stride, const uint32_t* __restrict__ offsets,
+                      const uint32_t* __restrict__ ends, const uint2* __restrict__ sorted, const uint32_t* __restrict__ total_refs_p, XYZZ<Fq>* __restrict__ buckets, XYZZ<Fq>* __restrict__ part_pt,
+                      uint32_t* __restrict__ part_bkt) {
+  const uint32_t total = *total_refs_p;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t start64 = (uint64_t)t * MSM_Q;
+  // partial slots 2t (head) and 2t+1 (tail) default to "none"
+  uint32_t head_b = MSM_NO_DIGIT, tail_b = MSM_NO_DIGIT;
+  if (start64 < total) {
+    const uint32_t start = (uint32_t)start64;
+    const uint32_t end = (total - start > (uint32_t)MSM_Q) ? start + MSM_Q : total;
+    uint2 rb = __ldg(sorted + start);
+    uint32_t ref = rb.x;
+    uint32_t cur_b = rb.y;
+    uint32_t seg_start = start;
+    Affine<Fq> p = ld_affine(tables + (size_t)((ref >> MSM_IDX_BITS) & 31u) * table_stride + (ref & ((1u << MSM_IDX_BITS) - 1)));
+    XYZZ<Fq> acc = XYZZ<Fq>::inf();
     for (uint32_t e = start; e < end; e++) {
       Affine<Fq> cur = p;
-      bool neg = ref >> 31;
+      const bool neg = ref >> 31;
+      uint32_t next_b = cur_b;
       if (e + 1 < end) {
-        ref = sorted[e + 1];
-        p = ld_affine(tables + (size_t)((ref >> MSM_IDX_BITS) & 31u) * table_stride + base_off + (ref & ((1u << MSM_IDX_BITS) - 1)));
+        rb = __ldg(sorted + e + 1);
+        ref = rb.x;
+        next_b = rb.y;
+        p = ld_affine(tables + (size_t)((ref >> MSM_IDX_BITS) & 31u) * table_stride + (ref & ((1u << MSM_IDX_BITS) - 1)));
       }
       acc.add_mixed(cur, neg);
+      if (e + 1 == end || next_b != cur_b) {
+        // run [seg_start, e] of bucket cur_b ends here
+        const bool whole = (seg_start == offsets[cur_b]) && (e + 1 == ends[cur_b]);
+        if (whole) {
+          st_words(buckets + cur_b, acc);
+        } else if (seg_start == start && head_b == MSM_NO_DIGIT) {
+          st_words(part_pt + 2 * (size_t)t, acc);
+          head_b = cur_b;
+        } else {
+          st_words(part_pt + 2 * (size_t)t + 1, acc);
+          tail_b = cur_b;
+        }
+        acc = XYZZ<Fq>::inf();
+        seg_start = e + 1;
+        cur_b = next_b;
+      }
     }
+  }
+  part_bkt[2 * (size_t)t] = head_b;
+  part_bkt[2 * (size_t)t + 1] = tail_b;
+}
+// Partials are ordered by bucket (they follow the sorted references); the first partial of each bucket
+// sums the ones that follow it and stores the bucket.
+template <class Fq>
+__global__ void __launch_bounds__(128)
+msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nparts, XYZZ<Fq>* buckets) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= nparts) return;
+  const uint32_t b = part_bkt[i];
+  if (b == MSM_NO_DIGIT) return;
+  // leader = no earlier partial of the same bucket (an intervening empty slot is possible: look back two)
+  if (i >= 1 && part_bkt[i - 1] == b) return;
+  if (i >= 2 && part_bkt[i - 1] == MSM_NO_DIGIT && part_bkt[i - 2] == b) return;
+  XYZZ<Fq> acc = ld_words(part_pt + i);
+  for (size_t k = i + 1; k < nparts; k++) {
+    uint32_t bk = part_bkt[k];
+    if (bk == MSM_NO_DIGIT) continue;
+    if (bk != b) break;
+    g1_add(acc, ld_words(part_pt + k));
   }
   st_words(buckets + b, acc);
 }
+static __global__ void msm_total_kernel(const uint32_t* cursor, uint32_t B, uint32_t* total) { *total = cursor[B - 1]; }
 
 // ---- 5. reduce ----------------------------------------------------------------------------------
-// Level kernel: thread j owns in[j*L .. j*L+L):  S[j] = sum_i in[..+i],  T0 = sum_i i * in[..+i];
-// block_t[blockIdx] = sum over the block's threads of T0.   W0(in) = L * W0(S) + sum_j T0_j.
-template <class Fq>
-__global__ void __launch_bounds__(MSM_RED_THREADS)
-msm_seg_reduce_kernel(const XYZZ<Fq>* in, uint32_t m, uint32_t L, XYZZ<Fq>* S, XYZZ<Fq>* block_t) {
-  __shared__ uint4 sm_raw[MSM_RED_THREADS * sizeof(XYZZ<Fq>) / 16];
-  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(sm_raw);
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t nseg = m / L;
-  XYZZ<Fq> running = XYZZ<Fq>::inf(), acc = XYZZ<Fq>::inf();
-  if (j < nseg) {
-    const XYZZ<Fq>* seg = in + (size_t)j * L;
-    for (uint32_t i = L - 1; i >= 1; i--) {
-      g1_add(running, ld_words(seg + i));
-      g1_add(acc, running);
-    }
-    g1_add(running, ld_words(seg));
-    st_words(S + j, running);
-  }
-  sm[threadIdx.x] = acc;
-  __syncthreads();
-  for (int s = MSM_RED_THREADS / 2; s >= 1; s >>= 1) {
-    if ((int)threadIdx.x < s) {
-      XYZZ<Fq> a = sm[threadIdx.x];
-      g1_add(a, sm[threadIdx.x + s]);
-      sm[threadIdx.x] = a;
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) st_words(block_t + blockIdx.x, sm[0]);
-}
+// sum_b (b + 1) B_b for a BATCH of bucket arrays at once (the MSMs of one commit round), built from
+// log-depth trees so that the latency-bound tail is paid once per round, not once per MSM.
+// View bucket index b = hi * L + lo  (R = B / L rows of L columns):
+//     sum_b b B_b = L * sum_hi hi * Rsum[hi] + sum_lo lo * Csum[lo],
+//     Rsum[hi] = sum_lo B[hi][lo]  (row tree),   Csum[lo] = sum_hi B[hi][lo]  (column tree),
+// and each of the two short weighted sums is done by bit planes: sum_i i V_i = sum_k 2^k sum_{i: bit k} V_i.
 
-// result = top_sum + U_0 + L_0 * (U_1 + L_1 * (U_2 + ...)),  U_l = sum of level l's partials.
-// extra[0..n_extra) are further XYZZ terms added in (hiding commitments, partial results).
+// out[g][i] = in[g][2i] + in[g][2i+1]     (g < groups, i < len / 2)
 template <class Fq>
-__global__ void __launch_bounds__(256)
-msm_finish_kernel(MsmLevels levels, const XYZZ<Fq>* top_sum, const XYZZ<Fq>* extra, int n_extra, XYZZ<Fq>* out_xyzz,
-                  Affine<Fq>* out_affine) {
+__global__ void __launch_bounds__(128) msm_pair_rows_kernel(const XYZZ<Fq>* in, XYZZ<Fq>* out, size_t groups, size_t len) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t half = len >> 1;
+  if (t >= groups * half) return;
+  size_t g = t / half, i = t - g * half;
+  XYZZ<Fq> a = ld_words(in + g * len + 2 * i);
+  g1_add(a, ld_words(in + g * len + 2 * i + 1));
+  st_words(out + t, a);
+}
+// out[j][h][lo] = in[j][2h][lo] + in[j][2h+1][lo]   (j < nj, h < rows / 2, lo < L)
+template <class Fq>
+__global__ void __launch_bounds__(128) msm_pair_cols_kernel(const XYZZ<Fq>* in, XYZZ<Fq>* out, size_t nj, size_t rows, size_t L) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t hr = rows >> 1;
+  if (t >= nj * hr * L) return;
+  size_t lo = t % L, jh = t / L, j = jh / hr, h = jh - j * hr;
+  const XYZZ<Fq>* p = in + ((j * rows + 2 * h) * L + lo);
+  XYZZ<Fq> a = ld_words(p);
+  g1_add(a, ld_words(p + L));
+  st_words(out + t, a);
+}
+// planes[j][p] for p in [0, nbits]: p < nbits -> sum of V[j][i] over i with bit p set; p == nbits -> sum of all.
+template <class Fq>
+__global__ void __launch_bounds__(256) msm_bitplane_kernel(const XYZZ<Fq>* v, size_t len, int nbits, XYZZ<Fq>* planes) {
   __shared__ uint4 sm_raw[256 * sizeof(XYZZ<Fq>) / 16];
   XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(sm_raw);
-  XYZZ<Fq> total = XYZZ<Fq>::inf();
-  for (int lv = levels.n - 1; lv >= 0; lv--) {
-    const XYZZ<Fq>* part = reinterpret_cast<const XYZZ<Fq>*>(levels.lv[lv].partials);
-    XYZZ<Fq> a = XYZZ<Fq>::inf();
-    for (uint32_t i = threadIdx.x; i < levels.lv[lv].count; i += 256) g1_add(a, ld_words(part + i));
-    sm[threadIdx.x] = a;
-    __syncthreads();
-    for (int s = 128; s >= 1; s >>= 1) {
-      if ((int)threadIdx.x < s) {
-        XYZZ<Fq> t = sm[threadIdx.x];
-        g1_add(t, sm[threadIdx.x + s]);
-        sm[threadIdx.x] = t;
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      // total = U_lv + L_lv * total
-      for (uint32_t k = 0; k < levels.lv[lv].log_l; k++) g1_dbl(total);
-      g1_add(total, sm[0]);
+  const int p = blockIdx.x;
+  const size_t j = blockIdx.y;
+  const XYZZ<Fq>* vec = v + j * len;
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+  for (size_t i = threadIdx.x; i < len; i += 256)
+    if (p == nbits || ((i >> p) & 1)) g1_add(acc, ld_words(vec + i));
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s >= 1; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      XYZZ<Fq> t = sm[threadIdx.x];
+      g1_add(t, sm[threadIdx.x + s]);
+      sm[threadIdx.x] = t;
     }
     __syncthreads();
   }
+  if (threadIdx.x == 0) st_words(planes + j * (nbits + 1) + p, sm[0]);
+}
+struct MsmFinishJob {
+  const void* extra;  // XYZZ[n_extra] further terms (hiding commitments, shifted parts)
+  int n_extra;
+  void* out_xyzz;     // XYZZ* or null
+  void* out_affine;   // Affine* or null
+};
+constexpr int MSM_MAX_BATCH = 8;
+struct MsmFinishJobs {
+  MsmFinishJob j[MSM_MAX_BATCH];
+};
+// One block per job: warp 0 folds the row planes, warp 1 the column planes (Horner over the bits), then
+// result = L * Wr + Wc + (sum of all buckets) + extras.  has_buckets = 0: only the extras (empty MSM).
+template <class Fq>
+__global__ void __launch_bounds__(64) msm_finish_kernel(const XYZZ<Fq>* rplanes, int rbits, const XYZZ<Fq>* cplanes, int cbits,
+                                                        int has_buckets, MsmFinishJobs jobs) {
+  __shared__ uint4 sm_raw[2 * sizeof(XYZZ<Fq>) / 16];
+  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(sm_raw);
+  const int j = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    XYZZ<Fq> acc = XYZZ<Fq>::inf();
+    if (has_buckets) {
+      const XYZZ<Fq>* pl = warp == 0 ? rplanes + (size_t)j * (rbits + 1) : cplanes + (size_t)j * (cbits + 1);
+      int nb = warp == 0 ? rbits : cbits;
+      for (int k = nb - 1; k >= 0; k--) {
+        g1_dbl(acc);
+        g1_add(acc, ld_words(pl + k));
+      }
+      if (warp == 0) {
+        for (int k = 0; k < cbits; k++) g1_dbl(acc);   // * L
+        g1_add(acc, ld_words(pl + rbits));               // + sum of all buckets (weights are b + 1)
+      }
+    }
+    sm[warp] = acc;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    if (top_sum) g1_add(total, ld_words(top_sum));
-    for (int i = 0; i < n_extra; i++) g1_add(total, ld_words(extra + i));
-    if (out_xyzz) st_words(out_xyzz, total);
-    if (out_affine) st_words(out_affine, g1_to_affine(total));
+    XYZZ<Fq> total = sm[0];
+    g1_add(total, sm[1]);
+    const XYZZ<Fq>* extra = reinterpret_cast<const XYZZ<Fq>*>(jobs.j[j].extra);
+    for (int i = 0; i < jobs.j[j].n_extra; i++) g1_add(total, ld_words(extra + i));
+    if (jobs.j[j].out_xyzz) st_words(reinterpret_cast<XYZZ<Fq>*>(jobs.j[j].out_xyzz), total);
+    if (jobs.j[j].out_affine) st_words(reinterpret_cast<Affine<Fq>*>(jobs.j[j].out_affine), g1_to_affine(total));
   }
 }
 
@@ -257,15 +348,17 @@ int Msm<Fr, Fq>::pick_window(size_t n) {
 }
 
 template <class Fr, class Fq>
-Msm<Fr, Fq>::Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, int window_bits) : ctx(&cx), n_srs(n) {
-  B2M_REQUIRE(n >= 1 && n <= ((size_t)1 << MSM_IDX_BITS), B2M_ERR_INVALID_ARG, "SRS size %zu out of range", n);
+Msm<Fr, Fq>::Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, const Affine<Fq>* host_extra, size_t n_extra_bases, int window_bits)
+    : ctx(&cx), n_srs(n), n_extra(n_extra_bases), stride(n + n_extra_bases) {
+  B2M_REQUIRE(n >= 1 && stride <= ((size_t)1 << MSM_IDX_BITS), B2M_ERR_INVALID_ARG, "SRS size %zu out of range", n);
   c = window_bits > 0 ? window_bits : pick_window(n);
   B2M_REQUIRE(c >= MSM_MIN_WINDOW && c <= 24, B2M_ERR_INVALID_ARG, "window bits %d out of range [%d, 24]", c, MSM_MIN_WINDOW);
   W = (Fr::Params::BITS + 1 + c - 1) / c;
   B2M_REQUIRE(W <= 32, B2M_ERR_INVALID_ARG, "too many windows (%d)", W);
-  tables = DBuf<Affine<Fq>>(cx, (size_t)W * n);
+  tables = DBuf<Affine<Fq>>(cx, (size_t)W * stride);
   tables.upload(host_powers, n);
-  msm_precompute_kernel<Fq><<<div_up(n, 128), 128, 0, cx.stream>>>(tables.p, n, c, W);
+  if (n_extra) B2M_CUDA(cudaMemcpyAsync(tables.p + n, host_extra, n_extra * sizeof(Affine<Fq>), cudaMemcpyHostToDevice, cx.stream));
+  msm_precompute_kernel<Fq><<<div_up(stride, 128), 128, 0, cx.stream>>>(tables.p, stride, c, W);
   B2M_CHECK_LAUNCH();
   cx.launches++;
   cx.sync();
@@ -274,61 +367,110 @@ Msm<Fr, Fq>::Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, int window_bi
 template <class Fr, class Fq>
 void Msm<Fr, Fq>::run(const Fr* scalars, bool mont, size_t n, size_t base_off, const XYZZ<Fq>* extra, int n_extra,
                       XYZZ<Fq>* out_xyzz, Affine<Fq>* out_affine) {
-  B2M_REQUIRE(base_off + n <= n_srs, B2M_ERR_DEGREE_TOO_LARGE, "MSM slice [%zu, %zu) exceeds the SRS (%zu powers)", base_off,
-              base_off + n, n_srs);
+  MsmJob<Fr, Fq> job{scalars, mont, n, base_off, nullptr, 0, 0, extra, n_extra, out_xyzz, out_affine};
+  run_batch(&job, 1);
+}
+
+template <class Fr, class Fq>
+void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs, int nj) {
   Ctx& cx = *ctx;
-  MsmLevels levels;
-  levels.n = 0;
-  if (n == 0) {
-    msm_finish_kernel<Fq><<<1, 256, 0, cx.stream>>>(levels, nullptr, extra, n_extra, out_xyzz, out_affine);
+  B2M_REQUIRE(nj >= 1 && nj <= MSM_MAX_BATCH, B2M_ERR_INVALID_ARG, "MSM batch of %d jobs", nj);
+  size_t max_n = 0;
+  for (int j = 0; j < nj; j++) {
+    B2M_REQUIRE(jobs[j].base_off + jobs[j].n <= n_srs, B2M_ERR_DEGREE_TOO_LARGE, "MSM slice [%zu, %zu) exceeds the SRS (%zu powers)",
+                jobs[j].base_off, jobs[j].base_off + jobs[j].n, n_srs);
+    B2M_REQUIRE(jobs[j].n2 == 0 || jobs[j].extra_base + jobs[j].n2 <= n_extra, B2M_ERR_INVALID_ARG, "extra bases out of range");
+    max_n = std::max(max_n, jobs[j].n + jobs[j].n2);
+  }
+  MsmFinishJobs fj;
+  for (int j = 0; j < nj; j++) fj.j[j] = MsmFinishJob{jobs[j].extra, jobs[j].n_extra, jobs[j].out_xyzz, jobs[j].out_affine};
+  if (max_n == 0) {
+    msm_finish_kernel<Fq><<<nj, 64, 0, cx.stream>>>(nullptr, 0, nullptr, 0, 0, fj);
     B2M_CHECK_LAUNCH();
     cx.launches++;
     return;
   }
   const uint32_t B = 1u << (c - 1);
-  DBuf<uint32_t> digits(cx, (size_t)W * n), hist(cx, B), offsets(cx, B), cursor(cx, B), sorted(cx, (size_t)W * n);
-  hist.zero();
-  size_t sp0 = cx.span_begin("msm_sort", (double)n);
-  msm_digits_kernel<Fr><<<div_up(n, 256), 256, 0, cx.stream>>>(scalars, mont, n, c, W, digits.p, hist.p);
-  B2M_CHECK_LAUNCH();
-  cx.launches++;
-  exclusive_scan_u32(cx, hist.p, offsets.p, B);
-  B2M_CUDA(cudaMemcpyAsync(cursor.p, offsets.p, B * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
-  msm_scatter_kernel<<<div_up(n, 256), 256, 0, cx.stream>>>(digits.p, n, W, cursor.p, sorted.p);
-  B2M_CHECK_LAUNCH();
-  cx.launches++;
-  cx.span_end(sp0);
-  DBuf<XYZZ<Fq>> buckets(cx, B);
-  size_t sp = cx.span_begin("msm_accumulate_kernel", (double)n);
-  msm_accumulate_kernel<Fq><<<div_up(B, 128), 128, 0, cx.stream>>>(tables.p, n_srs, base_off, offsets.p, cursor.p, sorted.p, B,
-                                                                    buckets.p);
-  B2M_CHECK_LAUNCH();
-  cx.launches++;
-  cx.span_end(sp);
-  size_t sp2 = cx.span_begin("msm_reduce", (double)n);
-
-  // hierarchical reduction: W0(A) = L * W0(S) + sum T0, level by level
-  std::vector<DBuf<XYZZ<Fq>>> keep;
-  const XYZZ<Fq>* cur = buckets.p;
-  uint32_t m = B;
-  while (m > 1) {
-    uint32_t L = m >= (uint32_t)MSM_SEG ? (uint32_t)MSM_SEG : m;
-    uint32_t nseg = m / L;
-    uint32_t grid = (nseg + MSM_RED_THREADS - 1) / MSM_RED_THREADS;
-    DBuf<XYZZ<Fq>> S(cx, nseg), part(cx, grid);
-    msm_seg_reduce_kernel<Fq><<<grid, MSM_RED_THREADS, 0, cx.stream>>>(cur, m, L, S.p, part.p);
-    B2M_CHECK_LAUNCH();
-    cx.launches++;
-    B2M_REQUIRE(levels.n < MSM_MAX_LEVELS, B2M_ERR_INVALID_ARG, "too many reduction levels");
-    int lg = 0;
-    while ((1u << lg) < L) lg++;
-    levels.lv[levels.n++] = MsmLevel{part.p, grid, (uint32_t)lg};
-    cur = S.p;
-    m = nseg;
-    keep.push_back(std::move(S));
-    keep.push_back(std::move(part));
+  const int cbits = (c - 1 + 1) / 2, rbits = (c - 1) - cbits;  // L = 2^cbits columns, R = 2^rbits rows
+  const size_t L = (size_t)1 << cbits, R = (size_t)1 << rbits;
+  DBuf<XYZZ<Fq>> buckets(cx, (size_t)nj * B);
+  {
+    // sort + accumulate, one job after the other (both saturate the chip)
+    const size_t max_refs = (size_t)W * max_n;
+    const size_t max_threads = (max_refs + MSM_Q - 1) / MSM_Q + 256;  // launches round up to whole blocks
+    DBuf<uint32_t> digits(cx, max_refs), hist(cx, B), offsets(cx, B), cursor(cx, B);
+    DBuf<uint2> sorted(cx, max_refs);
+    DBuf<uint32_t> total(cx, 1), part_bkt(cx, 2 * max_threads);
+    DBuf<XYZZ<Fq>> part_pt(cx, 2 * max_threads);
+    buckets.zero();  // empty buckets are never written: all-zero XYZZ is the point at infinity
+    for (int j = 0; j < nj; j++) {
+      const size_t n = jobs[j].n, nt = jobs[j].n + jobs[j].n2;
+      if (nt == 0) continue;
+      hist.zero();
+      size_t sp0 = cx.span_begin("msm_sort", (double)n);
+      msm_digits_kernel<Fr><<<div_up(nt, 256), 256, 0, cx.stream>>>(jobs[j].scalars, jobs[j].scalars2, jobs[j].mont, n, nt, c, W, digits.p,
+                                                                    hist.p);
+      B2M_CHECK_LAUNCH();
+      exclusive_scan_u32(cx, hist.p, offsets.p, B);
+      B2M_CUDA(cudaMemcpyAsync(cursor.p, offsets.p, B * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
+      msm_scatter_kernel<<<div_up(nt, 256), 256, 0, cx.stream>>>(digits.p, n, nt, jobs[j].base_off, n_srs + jobs[j].extra_base, W, cursor.p,
+                                                                  sorted.p);
+      msm_total_kernel<<<1, 1, 0, cx.stream>>>(cursor.p, B, total.p);
+      B2M_CHECK_LAUNCH();
+      cx.launches += 3;
+      cx.span_end(sp0);
+      size_t sp = cx.span_begin("msm_accumulate_kernel", (double)n);
+      const size_t nthreads = ((size_t)W * nt + MSM_Q - 1) / MSM_Q;  // upper bound on ceil(total_refs / Q)
+      msm_accumulate_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(tables.p, stride, offsets.p, cursor.p, sorted.p, total.p,
+                                                                               buckets.p + (size_t)j * B, part_pt.p, part_bkt.p);
+      B2M_CHECK_LAUNCH();
+      cx.launches++;
+      cx.span_end(sp);
+      size_t nparts = 2 * (size_t)div_up(nthreads, 128) * 128;
+      msm_stitch_kernel<Fq><<<div_up(nparts, 128), 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, nparts, buckets.p + (size_t)j * B);
+      B2M_CHECK_LAUNCH();
+      cx.launches++;
+    }
   }
-  msm_finish_kernel<Fq><<<1, 256, 0, cx.stream>>>(levels, cur, extra, n_extra, out_xyzz, out_affine);
+  double units = 0;
+  for (int j = 0; j < nj; j++) units += (double)jobs[j].n;
+  size_t sp2 = cx.span_begin("msm_reduce", units);
+  DBuf<XYZZ<Fq>> ping(cx, (size_t)nj * B / 2 + 1), pong(cx, (size_t)nj * B / 4 + 1);
+  DBuf<XYZZ<Fq>> rsum(cx, (size_t)nj * R), csum(cx, (size_t)nj * L);
+  auto tree = [&](bool rows_tree) {
+    const XYZZ<Fq>* cur = buckets.p;
+    size_t len = rows_tree ? L : R;  // extent being folded
+    XYZZ<Fq>* bufs[2] = {ping.p, pong.p};
+    int which = 0;
+    if (len == 1) {  // nothing to fold: the sums are the buckets themselves
+      B2M_CUDA(cudaMemcpyAsync(rows_tree ? rsum.p : csum.p, cur, (size_t)nj * B * sizeof(XYZZ<Fq>), cudaMemcpyDeviceToDevice, cx.stream));
+      return;
+    }
+    while (len > 1) {
+      XYZZ<Fq>* out = (len == 2) ? (rows_tree ? rsum.p : csum.p) : bufs[which];
+      size_t threads;
+      if (rows_tree) {
+        threads = (size_t)nj * R * (len / 2);
+        msm_pair_rows_kernel<Fq><<<div_up(threads, 128), 128, 0, cx.stream>>>(cur, out, (size_t)nj * R, len);
+      } else {
+        threads = (size_t)nj * (len / 2) * L;
+        msm_pair_cols_kernel<Fq><<<div_up(threads, 128), 128, 0, cx.stream>>>(cur, out, (size_t)nj, len, L);
+      }
+      B2M_CHECK_LAUNCH();
+      cx.launches++;
+      cur = out;
+      which ^= 1;
+      len >>= 1;
+    }
+  };
+  tree(true);
+  tree(false);
+  DBuf<XYZZ<Fq>> rplanes(cx, (size_t)nj * (rbits + 1)), cplanes(cx, (size_t)nj * (cbits + 1));
+  msm_bitplane_kernel<Fq><<<dim3(rbits + 1, nj), 256, 0, cx.stream>>>(rsum.p, R, rbits, rplanes.p);
+  msm_bitplane_kernel<Fq><<<dim3(cbits + 1, nj), 256, 0, cx.stream>>>(csum.p, L, cbits, cplanes.p);
+  B2M_CHECK_LAUNCH();
+  cx.launches += 2;
+  msm_finish_kernel<Fq><<<nj, 64, 0, cx.stream>>>(rplanes.p, rbits, cplanes.p, cbits, 1, fj);
   B2M_CHECK_LAUNCH();
   cx.launches++;
   cx.span_end(sp2);

@@ -249,7 +249,9 @@ struct MarlinIndex : IndexBase {
     // commit to the index polynomials, rng = None [reference lib.rs:124-125]
     {
       DBuf<Pt> out(cx, 6);
-      for (int i = 0; i < 6; i++) msm.run(ipoly[i].p, true, K, 0, nullptr, 0, nullptr, out.p + i);
+      MsmJob<Fr, Fq> jobs[6];
+      for (int i = 0; i < 6; i++) jobs[i] = MsmJob<Fr, Fq>{ipoly[i].p, true, K, 0, nullptr, 0, 0, nullptr, 0, nullptr, out.p + i};
+      msm.run_batch(jobs, 6);
       out.download(index_comms, 6);
     }
     comms_xy.resize(6 * 2 * LQ);
@@ -358,22 +360,17 @@ struct MarlinIndex : IndexBase {
     return h;
   }
 
-  // One KZG10::commit: MSM over powers_of_g[off..off+len) plus the blinding polynomial over the gamma
-  // powers starting at gamma slot `gslot`; result (affine) written to out_dev.
-  void kzg_commit(const Fr* coeffs, size_t len, size_t off, const HPoly& blinding, size_t gslot, Pt* out_dev,
-                  std::vector<DBuf<Fr>>& keep_sc, std::vector<DBuf<Xy>>& keep_pt) {
-    const Xy* extra = nullptr;
-    int n_extra = 0;
+  // One KZG10::commit as an MSM job: powers_of_g[off..off+len) against the coefficients, and the blinding
+  // polynomial against the gamma powers starting at gamma slot `gslot` -- all in the same bucket pass.
+  MsmJob<Fr, Fq> kzg_commit_job(const Fr* coeffs, size_t len, size_t off, const HPoly& blinding, size_t gslot, Pt* out_dev,
+                                std::vector<DBuf<Fr>>& keep_sc) {
+    const Fr* s2 = nullptr;
     if (!blinding.empty()) {
       keep_sc.emplace_back(cx, blinding.size());
-      keep_pt.emplace_back(cx, 1);
       keep_sc.back().upload(blinding.data(), blinding.size());
-      msm.run_small(reinterpret_cast<const Pt*>(srs->gamma_dev) + gslot, keep_sc.back().p, true, (int)blinding.size(),
-                    keep_pt.back().p);
-      extra = keep_pt.back().p;
-      n_extra = 1;
+      s2 = keep_sc.back().p;
     }
-    msm.run(coeffs, true, len, off, extra, n_extra, nullptr, out_dev);
+    return MsmJob<Fr, Fq>{coeffs, true, len, off, s2, blinding.size(), gslot, nullptr, 0, nullptr, out_dev};
   }
 
   struct Oracle {       // a labelled polynomial living in HBM
@@ -389,8 +386,8 @@ struct MarlinIndex : IndexBase {
   // `PC::commit` over a round's oracles, drawing blinding polynomials from zk in the reference's order.
   void commit_round(std::vector<Oracle*>& polys, ChaChaHost& zk) {
     std::vector<DBuf<Fr>> keep_sc;
-    std::vector<DBuf<Xy>> keep_pt;
     DBuf<Pt> out(cx, 2 * polys.size());
+    std::vector<MsmJob<Fr, Fq>> jobs;
     for (size_t i = 0; i < polys.size(); i++) {
       Oracle& o = *polys[i];
       auto draw = [&]() {
@@ -401,26 +398,34 @@ struct MarlinIndex : IndexBase {
       };
       if (pc == B2M_PC_MARLIN_KZG10) {
         o.rand = draw();
-        kzg_commit(o.p, o.len, 0, o.rand, srs->gamma_slot(0), out.p + 2 * i, keep_sc, keep_pt);
+        jobs.push_back(kzg_commit_job(o.p, o.len, 0, o.rand, srs->gamma_slot(0), out.p + 2 * i, keep_sc));
         if (o.bounded) {
           o.shifted_rand = draw();
-          kzg_commit(o.p, o.len, shifted_off(o.bound), o.shifted_rand, srs->gamma_slot(0), out.p + 2 * i + 1, keep_sc, keep_pt);
+          jobs.push_back(kzg_commit_job(o.p, o.len, shifted_off(o.bound), o.shifted_rand, srs->gamma_slot(0), out.p + 2 * i + 1, keep_sc));
         }
       } else {
         o.rand = draw();
         if (o.bounded)
-          kzg_commit(o.p, o.len, shifted_off(o.bound), o.rand, o.hiding ? srs->gamma_slot(D - o.bound) : 0, out.p + 2 * i, keep_sc,
-                     keep_pt);
+          jobs.push_back(kzg_commit_job(o.p, o.len, shifted_off(o.bound), o.rand, o.hiding ? sonic_gamma_slot(o.bound) : 0,
+                                        out.p + 2 * i, keep_sc));
         else
-          kzg_commit(o.p, o.len, 0, o.rand, o.hiding ? srs->gamma_slot(0) : 0, out.p + 2 * i, keep_sc, keep_pt);
+          jobs.push_back(kzg_commit_job(o.p, o.len, 0, o.rand, o.hiding ? srs->gamma_slot(0) : 0, out.p + 2 * i, keep_sc));
       }
     }
+    msm.run_batch(jobs.data(), (int)jobs.size());
     std::vector<Pt> h(2 * polys.size());
     out.download(h.data(), h.size());
     for (size_t i = 0; i < polys.size(); i++) {
       polys[i]->comm = h[2 * i];
       polys[i]->shifted_comm = h[2 * i + 1];
     }
+  }
+  // sonic_pc shifted_powers_of_gamma_g[bound]: powers max_degree - bound + {0, 1, 2} in consecutive slots
+  size_t sonic_gamma_slot(size_t bound) const {
+    size_t s0 = srs->gamma_slot(D - bound);
+    for (size_t i = 1; i < 3; i++)
+      B2M_REQUIRE(srs->gamma_slot(D - bound + i) == s0 + i, B2M_ERR_INVALID_ARG, "gamma powers for bound %zu are not consecutive", bound);
+    return s0;
   }
   void absorb_comms(FiatShamir& fs, std::vector<Oracle*>& polys) {
     std::vector<uint8_t> bytes;
@@ -736,6 +741,7 @@ struct MarlinIndex : IndexBase {
     const Fr ch_outer = marlin ? xp[2] : xp[1], ch_t = marlin ? xp[3] : xp[2], ch_zb = marlin ? xp[4] : xp[3];
     const Fr ch_inner = marlin ? xp[2] : xp[1];
     DBuf<Pt> w_out(cx, 2);
+    std::vector<MsmJob<Fr, Fq>> shifted_jobs, final_jobs;
     HPoly r_beta;       // combined hiding randomness at beta
     HPoly sr_beta;      // shifted randomness (Marlin PC): xi * shifted_rand(g_1)
     std::vector<DBuf<Fr>> keep_sc;
@@ -760,7 +766,6 @@ struct MarlinIndex : IndexBase {
       hp_axpy(r_beta, ch_outer, r_outer);
       hp_axpy(r_beta, ch_zb, o_zb.rand);
       HPoly hw = hp_is_zero(r_beta) ? HPoly() : hp_div_linear(r_beta, beta);  // hiding witness r / (X - beta)
-      std::vector<const Xy*> extras;
       DBuf<Xy> ex(cx, 2);
       int n_extra = 0;
       if (marlin) {
@@ -770,18 +775,19 @@ struct MarlinIndex : IndexBase {
         DBuf<Fr> sw(cx, o_g1.len);
         const Fr* ps = s_g1.p + 1; Fr* pd = sw.p; const Fr x1 = xp[1];
         ew(cx, o_g1.len - 1, [=] __device__(size_t i) { st_fr(pd + i, ld_fr(ps + i) * x1); });
-        msm.run(sw.p, true, o_g1.len - 1, shifted_off(o_g1.bound), nullptr, 0, ex.p + n_extra, nullptr);
+        shifted_jobs.push_back(MsmJob<Fr, Fq>{sw.p, true, o_g1.len - 1, shifted_off(o_g1.bound), nullptr, 0, 0, nullptr, 0, ex.p + n_extra,
+                                              nullptr});
         n_extra++;
         keep_sc.push_back(std::move(sw));
       }
+      const Fr* hw_dev = nullptr;
       if (!hw.empty()) {
         keep_sc.emplace_back(cx, hw.size());
         keep_sc.back().upload(hw.data(), hw.size());
-        msm.run_small(reinterpret_cast<const Pt*>(srs->gamma_dev) + srs->gamma_slot(0), keep_sc.back().p, true, (int)hw.size(),
-                      ex.p + n_extra);
-        n_extra++;
+        hw_dev = keep_sc.back().p;
       }
-      msm.run(sbeta.p + 1, true, 3 * H - 1, 0, ex.p, n_extra, nullptr, w_out.p);
+      final_jobs.push_back(MsmJob<Fr, Fq>{sbeta.p + 1, true, 3 * H - 1, 0, hw_dev, hw.size(), srs->gamma_slot(0), ex.p, n_extra, nullptr,
+                                          w_out.p});
       keep_pt.push_back(std::move(ex));
       keep_sc.push_back(std::move(pbeta));
       keep_sc.push_back(std::move(sbeta));
@@ -806,15 +812,18 @@ struct MarlinIndex : IndexBase {
         DBuf<Fr> sw(cx, o_g2.len);
         const Fr* ps = s_g2.p + 1; Fr* pd = sw.p; const Fr x1 = xp[1];
         ew(cx, o_g2.len - 1, [=] __device__(size_t i) { st_fr(pd + i, ld_fr(ps + i) * x1); });
-        msm.run(sw.p, true, o_g2.len - 1, shifted_off(o_g2.bound), nullptr, 0, ex.p, nullptr);
+        shifted_jobs.push_back(MsmJob<Fr, Fq>{sw.p, true, o_g2.len - 1, shifted_off(o_g2.bound), nullptr, 0, 0, nullptr, 0, ex.p, nullptr});
         n_extra = 1;
         keep_sc.push_back(std::move(sw));
       }
-      msm.run(sg.p + 1, true, K - 1, 0, ex.p, n_extra, nullptr, w_out.p + 1);
+      final_jobs.push_back(MsmJob<Fr, Fq>{sg.p + 1, true, K - 1, 0, nullptr, 0, 0, ex.p, n_extra, nullptr, w_out.p + 1});
       keep_pt.push_back(std::move(ex));
       keep_sc.push_back(std::move(pg));
       keep_sc.push_back(std::move(sg));
     }
+    // the shifted parts feed the final points as `extra` terms, so they form their own (earlier) batch
+    if (!shifted_jobs.empty()) msm.run_batch(shifted_jobs.data(), (int)shifted_jobs.size());
+    msm.run_batch(final_jobs.data(), (int)final_jobs.size());
     Pt w_pts[2];
     w_out.download(w_pts, 2);
     tm.end(t_op);
