@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--log-n", type=int, default=20, help="log2 of the number of constraints (BASELINE config 2: 20)")
     ap.add_argument("--pc", default="marlin_kzg10", choices=["marlin_kzg10", "sonic_kzg10"])
     ap.add_argument("--curve", default="bls12_381", choices=["bls12_381", "bn254"])
-    ap.add_argument("--cpu-log-n", type=int, default=14, help="instance size of the bounded CPU baseline sample")
+    ap.add_argument("--cpu-log-n", type=int, default=16, help="instance size of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

@@ -1,0 +1,70 @@
+"""ctypes wrapper of oracle/cport/libcport.so -- the C (OpenMP) restatement of the reference's CPU
+algorithms (ark-ec Pippenger MSM, ark-poly radix-2 FFT).  TEST INFRASTRUCTURE: tests/ use it as a
+fast checker; bench.py times it as the CPU baseline ("kind": "port")."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "libcport.so")
+_lib = None
+CURVE_ID = {"bls12_381": 0, "bn254": 1}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_PATH):
+            subprocess.check_call(["make", "-C", _HERE])
+        L = ctypes.CDLL(_PATH)
+        vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+        L.cport_msm.argtypes = [ci, vp, vp, sz, vp, ci]
+        L.cport_fft.argtypes = [ci, vp, ctypes.c_uint, ci, ci]
+        L.cport_gen_bases.argtypes = [ci, vp, sz, vp]
+        L.cport_prover_kernels.argtypes = [ci, ci, ctypes.c_uint, ci] + [ctypes.POINTER(ctypes.c_double)] * 4
+        L.cport_max_threads.restype = ci
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def msm(curve_name, bases_limbs, scalars_limbs, threads=0):
+    """bases: (n, 2*LQ) uint64 Montgomery affine; scalars: (n, 4) uint64 canonical -> (2*LQ,) uint64 affine."""
+    bases_limbs = np.ascontiguousarray(bases_limbs, dtype=np.uint64)
+    scalars_limbs = np.ascontiguousarray(scalars_limbs, dtype=np.uint64)
+    out = np.zeros(bases_limbs.shape[1], dtype=np.uint64)
+    lib().cport_msm(CURVE_ID[curve_name], _ptr(bases_limbs), _ptr(scalars_limbs), len(scalars_limbs), _ptr(out), threads)
+    return out
+
+
+def fft(curve_name, data_limbs, inverse=False, threads=0):
+    """in-place radix-2 FFT of (2^k, 4) uint64 Montgomery Fr limbs."""
+    n = len(data_limbs)
+    log_n = n.bit_length() - 1
+    assert 1 << log_n == n and data_limbs.flags["C_CONTIGUOUS"]
+    lib().cport_fft(CURVE_ID[curve_name], _ptr(data_limbs), log_n, 1 if inverse else 0, threads)
+    return data_limbs
+
+
+def prover_baseline(curve_name, pc, log_n, threads=0):
+    """CPU baseline for bench.py: seconds spent in the MSMs + FFTs of one 2^log_n-constraint proof."""
+    L = lib()
+    t_msm, t_fft, pairs, points = (ctypes.c_double() for _ in range(4))
+    nthreads = threads or L.cport_max_threads()
+    L.cport_prover_kernels(CURVE_ID[curve_name], 1 if pc == "sonic_kzg10" else 0, log_n, nthreads, ctypes.byref(t_msm),
+                           ctypes.byref(t_fft), ctypes.byref(pairs), ctypes.byref(points))
+    total = t_msm.value + t_fft.value
+    n = 1 << log_n
+    return {
+        "value": n / total, "unit": "constraints/s", "cores": nthreads, "kind": "port",
+        "sample": (f"C/OpenMP port of the reference's algorithms (ark-ec Pippenger: window ln(n)+2, one task per window; radix-2 FFT) "
+                   f"timed on the MSMs + FFTs of one {pc} proof of DummyCircuit 2^{log_n} ({int(pairs.value)} MSM pairs in "
+                   f"{t_msm.value:.2f} s, {int(points.value)} FFT points in {t_fft.value:.2f} s); pointwise passes excluded => "
+                   f"upper bound on the reference prover's speed"),
+        "seconds": total, "msm_seconds": t_msm.value, "fft_seconds": t_fft.value,
+    }
