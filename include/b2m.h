@@ -60,6 +60,13 @@ int b2m_ctx_create(int device, b2m_ctx** out);
 void b2m_ctx_destroy(b2m_ctx* ctx);
 /* Number of kernel launches issued through this context so far. */
 unsigned long long b2m_ctx_launches(const b2m_ctx* ctx);
+/* Multi-GPU MSM (one process per GPU of one node): rank 0 obtains an NCCL unique id (128 bytes), the
+ * caller broadcasts it, every rank attaches its context.  From then on every MSM issued through the
+ * context is sharded by (base, scalar) chunk across the ranks and the partial sums are exchanged with one
+ * all-gather; all ranks must issue the same sequence of calls. */
+int b2m_comm_unique_id(uint8_t* id, size_t cap);
+int b2m_ctx_attach_comm(b2m_ctx* ctx, const uint8_t* id, size_t id_len, int rank, int world);
+
 /* Per-kernel device timing (CUDA events on the context's stream) for the dominant kernels: enable,
  * run, then read {"kernel": {"launches", "ms", "units"}} -- units are (base, scalar) pairs for the MSM
  * kernels and points for the NTT.  Reading the report clears it. */

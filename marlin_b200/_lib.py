@@ -53,6 +53,8 @@ def lib():
         L.b2m_ctx_destroy.restype = None
         L.b2m_ctx_launches.argtypes = [vp]
         L.b2m_ctx_launches.restype = ctypes.c_ulonglong
+        L.b2m_comm_unique_id.argtypes = [vp, sz]
+        L.b2m_ctx_attach_comm.argtypes = [vp, vp, sz, ci, ci]
         L.b2m_ctx_profile.argtypes = [vp, ci]
         L.b2m_ctx_profile_report.argtypes = [vp, ctypes.c_char_p, sz]
         L.b2m_ntt.argtypes = [vp, ci, vp, ctypes.c_uint, ci, ci]

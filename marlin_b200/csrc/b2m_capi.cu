@@ -2,6 +2,7 @@
 // The prover-level entry points live in prover.cu.
 #include "capi_types.cuh"
 #include "prover.cuh"
+#include "comm.cuh"
 
 namespace b2m {
 thread_local std::string g_last_error;
@@ -25,10 +26,37 @@ void b2m_ctx_destroy(b2m_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cx.device);
   cudaStreamSynchronize(ctx->cx.stream);
+  if (ctx->cx.comm) NcclApi::get().CommDestroy(static_cast<ncclComm_t>(ctx->cx.comm));
   delete ctx;
 }
 
 unsigned long long b2m_ctx_launches(const b2m_ctx* ctx) { return ctx ? ctx->cx.launches : 0; }
+
+int b2m_comm_unique_id(uint8_t* id, size_t cap) {
+  return guard([&] {
+    B2M_REQUIRE(id && cap >= sizeof(ncclUniqueId), B2M_ERR_INVALID_ARG, "id buffer must hold %zu bytes", sizeof(ncclUniqueId));
+    ncclUniqueId u;
+    B2M_NCCL(NcclApi::get().GetUniqueId(&u));
+    memcpy(id, &u, sizeof(u));
+  });
+}
+
+int b2m_ctx_attach_comm(b2m_ctx* ctx, const uint8_t* id, size_t id_len, int rank, int world) {
+  return guard([&] {
+    B2M_REQUIRE(ctx && id && id_len >= sizeof(ncclUniqueId), B2M_ERR_INVALID_ARG, "bad unique id");
+    B2M_REQUIRE(world >= 1 && rank >= 0 && rank < world, B2M_ERR_INVALID_ARG, "bad rank %d / world %d", rank, world);
+    ctx->cx.use();
+    if (world > 1) {
+      ncclUniqueId u;
+      memcpy(&u, id, sizeof(u));
+      ncclComm_t comm;
+      B2M_NCCL(NcclApi::get().CommInitRank(&comm, world, u, rank));
+      ctx->cx.comm = comm;
+    }
+    ctx->cx.rank = rank;
+    ctx->cx.world = world;
+  });
+}
 
 int b2m_ctx_profile(b2m_ctx* ctx, int enable) {
   return guard([&] {

@@ -47,6 +47,9 @@ struct Ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaMemPool_t pool = nullptr;
+  // multi-GPU MSM sharding (comm.cuh): rank / world of this process and its ncclComm_t
+  int rank = 0, world = 1;
+  void* comm = nullptr;
   // kernel-launch counter (bench.py reports it as gpu_launches)
   unsigned long long launches = 0;
   // optional per-kernel timing (CUDA events on `stream`) for the roofline line of bench.py

@@ -3,6 +3,7 @@
 #include "msm.cuh"
 #include "devmem.cuh"
 #include "scan.cuh"
+#include "comm.cuh"
 
 namespace b2m {
 
@@ -301,6 +302,19 @@ __global__ void __launch_bounds__(64) msm_finish_kernel(const XYZZ<Fq>* rplanes,
   }
 }
 
+// Multi-GPU: out_j = sum_r partial[r][j] + extras (every rank computes the same sum in the same order).
+template <class Fq>
+__global__ void __launch_bounds__(32) msm_combine_kernel(const XYZZ<Fq>* all, int world, int nj, MsmFinishJobs jobs) {
+  const int j = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  XYZZ<Fq> total = XYZZ<Fq>::inf();
+  for (int r = 0; r < world; r++) g1_add(total, ld_words(all + (size_t)r * nj + j));
+  const XYZZ<Fq>* extra = reinterpret_cast<const XYZZ<Fq>*>(jobs.j[j].extra);
+  for (int i = 0; i < jobs.j[j].n_extra; i++) g1_add(total, ld_words(extra + i));
+  if (jobs.j[j].out_xyzz) st_words(reinterpret_cast<XYZZ<Fq>*>(jobs.j[j].out_xyzz), total);
+  if (jobs.j[j].out_affine) st_words(reinterpret_cast<Affine<Fq>*>(jobs.j[j].out_affine), g1_to_affine(total));
+}
+
 // ---- small MSM: one thread per term, double-and-add, block tree (n <= 256) -------------------
 template <class Fr, class Fq>
 __global__ void __launch_bounds__(256)
@@ -372,9 +386,33 @@ void Msm<Fr, Fq>::run(const Fr* scalars, bool mont, size_t n, size_t base_off, c
 }
 
 template <class Fr, class Fq>
-void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs, int nj) {
+void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
   Ctx& cx = *ctx;
   B2M_REQUIRE(nj >= 1 && nj <= MSM_MAX_BATCH, B2M_ERR_INVALID_ARG, "MSM batch of %d jobs", nj);
+  // Multi-GPU (comm.cuh): every rank holds the full window tables and the full scalar vectors (the prover
+  // runs replicated); rank r takes the r-th contiguous chunk of every MSM's (base, scalar) pairs, reduces
+  // it to one XYZZ point, and one all-gather of 192 B per MSM per rank exchanges the partial sums.
+  MsmJob<Fr, Fq> local[MSM_MAX_BATCH];
+  const bool sharded = cx.world > 1;
+  DBuf<XYZZ<Fq>> partial, gathered;
+  if (sharded) {
+    partial = DBuf<XYZZ<Fq>>(cx, nj);
+    gathered = DBuf<XYZZ<Fq>>(cx, (size_t)nj * cx.world);
+  }
+  for (int j = 0; j < nj; j++) {
+    local[j] = jobs_in[j];
+    if (sharded) {
+      size_t lo, hi;
+      shard_range(jobs_in[j].n, cx.rank, cx.world, &lo, &hi);
+      local[j].scalars = jobs_in[j].scalars + lo;
+      local[j].base_off = jobs_in[j].base_off + lo;
+      local[j].n = hi - lo;
+      if (cx.rank != 0) { local[j].scalars2 = nullptr; local[j].n2 = 0; }  // the blinding terms go to rank 0
+      local[j].extra = nullptr; local[j].n_extra = 0;
+      local[j].out_xyzz = partial.p + j; local[j].out_affine = nullptr;
+    }
+  }
+  const MsmJob<Fr, Fq>* jobs = local;
   size_t max_n = 0;
   for (int j = 0; j < nj; j++) {
     B2M_REQUIRE(jobs[j].base_off + jobs[j].n <= n_srs, B2M_ERR_DEGREE_TOO_LARGE, "MSM slice [%zu, %zu) exceeds the SRS (%zu powers)",
@@ -384,10 +422,22 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs, int nj) {
   }
   MsmFinishJobs fj;
   for (int j = 0; j < nj; j++) fj.j[j] = MsmFinishJob{jobs[j].extra, jobs[j].n_extra, jobs[j].out_xyzz, jobs[j].out_affine};
+  auto exchange = [&]() {  // multi-GPU: gather the per-rank partial sums and fold them (plus the extras) on every rank
+    if (!sharded) return;
+    size_t spx = cx.span_begin("msm_allgather", (double)nj);
+    all_gather_bytes(cx, partial.p, gathered.p, (size_t)nj * sizeof(XYZZ<Fq>));
+    MsmFinishJobs oj;
+    for (int j = 0; j < nj; j++) oj.j[j] = MsmFinishJob{jobs_in[j].extra, jobs_in[j].n_extra, jobs_in[j].out_xyzz, jobs_in[j].out_affine};
+    msm_combine_kernel<Fq><<<nj, 32, 0, cx.stream>>>(gathered.p, cx.world, nj, oj);
+    B2M_CHECK_LAUNCH();
+    cx.launches++;
+    cx.span_end(spx);
+  };
   if (max_n == 0) {
     msm_finish_kernel<Fq><<<nj, 64, 0, cx.stream>>>(nullptr, 0, nullptr, 0, 0, fj);
     B2M_CHECK_LAUNCH();
     cx.launches++;
+    exchange();
     return;
   }
   const uint32_t B = 1u << (c - 1);
@@ -474,6 +524,7 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs, int nj) {
   B2M_CHECK_LAUNCH();
   cx.launches++;
   cx.span_end(sp2);
+  exchange();
   // the DBufs are stream-ordered: their frees are enqueued behind the kernels above
 }
 
