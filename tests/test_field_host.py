@@ -1,0 +1,93 @@
+"""CPU: the device field / curve headers (csrc/field.cuh, curve.cuh) compiled for the host with an
+emulated carry flag, checked limb for limb against Python integers and the oracle's group law."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import ec
+from oracle.params import BLS12_381, BN254, BLS12_381_FR, BLS12_381_FQ, BN254_FR, BN254_FQ
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "host", "libfield_host.so")
+
+
+@pytest.fixture(scope="module")
+def hostlib():
+    src = os.path.join(HERE, "host", "field_host_shim.cpp")
+    if not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", src, "-o", SO])
+    return ctypes.CDLL(SO)
+
+
+@pytest.mark.parametrize("fi,field", list(enumerate([BLS12_381_FR, BLS12_381_FQ, BN254_FR, BN254_FQ])), ids=lambda x: getattr(x, "name", x))
+def test_montgomery_ops(hostlib, fi, field):
+    p = field.p
+    n = 8 if p.bit_length() <= 256 else 12
+    R = 1 << (32 * n)
+    Rinv = pow(R, -1, p)
+    A = ctypes.c_uint32 * n
+    rnd = random.Random(fi)
+
+    def call(w, a, b):
+        r = A()
+        hostlib.field_op(fi, w, A(*[(a >> (32 * i)) & 0xffffffff for i in range(n)]), A(*[(b >> (32 * i)) & 0xffffffff for i in range(n)]), r)
+        return sum(int(r[i]) << (32 * i) for i in range(n))
+
+    edge = [(0, 0), (1, p - 1), (p - 1, p - 1), (p - 2, 1), (R % p, R % p), ((p - 1) // 2, p - 1), (2, (p + 1) // 2), (p - 1, 0)]
+    for it in range(1500):
+        a, b = edge[it] if it < len(edge) else (rnd.randrange(p), rnd.randrange(p))
+        assert call(0, a, b) == a * b * Rinv % p
+        assert call(1, a, b) == (a + b) % p
+        assert call(2, a, b) == (a - b) % p
+        assert call(3, a, b) == (-a) % p
+        assert call(5, a, b) == a * Rinv % p
+        assert call(6, a, b) == a * R % p
+    for _ in range(3):
+        a = rnd.randrange(1, p)
+        assert call(4, a, 0) * a % p == R * R % p
+
+
+@pytest.mark.parametrize("ci,curve", list(enumerate([BLS12_381, BN254])), ids=lambda x: getattr(x, "name", x))
+def test_xyzz_group_law(hostlib, ci, curve):
+    fq = curve.fq
+    n32 = 12 if ci == 0 else 8
+    rnd = random.Random(5 + ci)
+
+    def pack(P):
+        if P is None:
+            return [0] * (2 * n32)
+        out = []
+        for v in P:
+            m = fq.to_mont(v)
+            out += [(m >> (32 * i)) & 0xffffffff for i in range(n32)]
+        return out
+
+    def unpack(arr):
+        x = sum(int(arr[i]) << (32 * i) for i in range(n32))
+        y = sum(int(arr[n32 + i]) << (32 * i) for i in range(n32))
+        return None if x == 0 and y == 0 else (fq.from_mont(x), fq.from_mont(y))
+
+    pts = [ec.scalar_mul(curve, rnd.randrange(1, curve.fr.p), curve.g) for _ in range(10)]
+    pts += [pts[0], pts[1], ec.affine_neg(curve, pts[2]), None, pts[0]]  # doubling, cancellation, infinity
+    out = (ctypes.c_uint32 * (2 * n32))()
+    for _ in range(10):
+        rnd.shuffle(pts)
+        neg = [rnd.randrange(2) for _ in pts]
+        flat = sum((pack(P) for P in pts), [])
+        A = (ctypes.c_uint32 * len(flat))(*flat)
+        NG = (ctypes.c_uint8 * len(pts))(*neg)
+        exp = None
+        for P, s in zip(pts, neg):
+            exp = ec.affine_add(curve, exp, ec.affine_neg(curve, P) if s else P)
+        for which in (0, 1):
+            hostlib.curve_op(ci, which, A, NG, len(pts), None, 0, out)
+            assert unpack(out) == exp
+    P = next(p for p in pts if p)
+    k = rnd.randrange(curve.fr.p)
+    K = (ctypes.c_uint32 * 8)(*[(k >> (32 * i)) & 0xffffffff for i in range(8)])
+    flat = pack(P)
+    hostlib.curve_op(ci, 2, (ctypes.c_uint32 * len(flat))(*flat), (ctypes.c_uint8 * 1)(0), 1, K, 8, out)
+    assert unpack(out) == ec.scalar_mul(curve, k, P)
