@@ -171,9 +171,10 @@ int cport_fft(int curve, u64* data, unsigned log_n, int inverse, int threads) {
  * are NOT included, so the figure is an upper bound on the reference prover's speed on this host. */
 static u64 rng_state = 0x9e3779b97f4a7c15ull;
 static u64 rnd64(void) { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return rng_state; }
-int cport_prover_kernels(int curve, int sonic, unsigned log_n, int threads, double* out_msm_s, double* out_fft_s, double* out_pairs, double* out_points) {
+int cport_prover_kernels(int curve, int sonic, unsigned log_n, int threads, int fft_threads, double* out_msm_s, double* out_fft_s, double* out_pairs, double* out_points) {
   init_all();
   if (threads <= 0) threads = max_threads();
+  if (fft_threads <= 0) fft_threads = threads;
   size_t H = (size_t)1 << log_n, K = 4 * H;
   const f4_ctx* fr = curve == 0 ? &BLS_FR : &BN_FR;
   /* MSM sizes (in coefficients): w, z_a, z_b, mask | t, g_1 (+shifted), h_1 | g_2 (+shifted), h_2 | open beta (+shifted), open gamma (+shifted) */
@@ -213,7 +214,7 @@ int cport_prover_kernels(int curve, int sonic, unsigned log_n, int threads, doub
   double tf = 0, points = 0;
   for (int g = 0; g < 4; g++) for (int r = 0; r < fcnt[g]; r++) {
     double t0 = now();
-    fr_fft(buf, flog[g], r & 1, fr, curve == 0 ? BLS_FR_GEN : BN_FR_GEN, curve == 0 ? BLS_FR_S : BN_FR_S, threads);
+    fr_fft(buf, flog[g], r & 1, fr, curve == 0 ? BLS_FR_GEN : BN_FR_GEN, curve == 0 ? BLS_FR_S : BN_FR_S, fft_threads);
     tf += now() - t0; points += (double)((size_t)1 << flog[g]);
   }
   free(buf); free(scal); free(bases);
