@@ -179,26 +179,95 @@ msm_accumulate_kernel(const Affine<Fq>* __restrict__ tables, size_t table_stride
   part_bkt[2 * (size_t)t] = head_b;
   part_bkt[2 * (size_t)t + 1] = tail_b;
 }
-// Partials are ordered by bucket (they follow the sorted references); the first partial of each bucket
-// sums the ones that follow it and stores the bucket.
+// Partials are ordered by bucket (they follow the sorted references).  The first partial of each bucket
+// sums the ones that follow it and stores the bucket; a bucket cut into many partials (skewed scalar
+// distributions, e.g. a polynomial whose coefficients are nearly all equal) is queued for
+// msm_stitch_long_kernel, which reduces it with a whole block.
+struct MsmLongRun {
+  uint32_t first, last, bucket;  // partial slots [first, last]
+};
 template <class Fq>
 __global__ void __launch_bounds__(128)
-msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nparts, XYZZ<Fq>* buckets) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= nparts) return;
-  const uint32_t b = part_bkt[i];
-  if (b == MSM_NO_DIGIT) return;
-  // leader = no earlier partial of the same bucket (an intervening empty slot is possible: look back two)
-  if (i >= 1 && part_bkt[i - 1] == b) return;
-  if (i >= 2 && part_bkt[i - 1] == MSM_NO_DIGIT && part_bkt[i - 2] == b) return;
-  XYZZ<Fq> acc = ld_words(part_pt + i);
-  for (size_t k = i + 1; k < nparts; k++) {
-    uint32_t bk = part_bkt[k];
-    if (bk == MSM_NO_DIGIT) continue;
-    if (bk != b) break;
-    g1_add(acc, ld_words(part_pt + k));
+msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nthreads, const uint32_t* offsets, const uint32_t* ends,
+                  XYZZ<Fq>* buckets, MsmLongRun* long_runs, uint32_t* n_long, uint32_t long_cap) {
+  // One thread per accumulate-thread u.  A run of partials starts either in u's tail slot (a bucket that
+  // begins inside u's range and continues into u + 1) or in u's head slot when the bucket begins exactly at
+  // u's first reference; u can hold only one of the two.  The common run is the pair (tail of u, head of
+  // u + 1): every lane does exactly one addition.  Longer runs go to msm_stitch_long_kernel.
+  size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (u >= nthreads) return;
+  uint32_t first = 2u * (uint32_t)u + 1u;
+  uint32_t b = part_bkt[first];
+  if (b == MSM_NO_DIGIT) {
+    first = 2u * (uint32_t)u;
+    b = part_bkt[first];
+    if (b == MSM_NO_DIGIT || offsets[b] != (uint32_t)u * (uint32_t)MSM_Q) return;  // not a run start
   }
+  const uint32_t t1 = (ends[b] - 1u) / (uint32_t)MSM_Q;  // thread holding the bucket's last reference
+  const uint32_t last = 2u * t1;                          // its head slot closes the run
+  if (t1 > (uint32_t)u + 1u) {
+    uint32_t slot = atomicAdd(n_long, 1u);
+    if (slot < long_cap) {
+      long_runs[slot] = MsmLongRun{first, last, b};
+      return;
+    }
+    XYZZ<Fq> acc = ld_words(part_pt + first);  // overflow of the queue: fold serially
+    for (uint32_t k = first + 1; k <= last; k++)
+      if (part_bkt[k] == b) g1_add(acc, ld_words(part_pt + k));
+    st_words(buckets + b, acc);
+    return;
+  }
+  XYZZ<Fq> acc = ld_words(part_pt + first);
+  g1_add(acc, ld_words(part_pt + last));
   st_words(buckets + b, acc);
+}
+// Runs longer than a pair (heavy buckets: e.g. the top window's digits of scalars < r only reach the low
+// 2^15 buckets).  One thread per queued run folds it serially -- all lanes busy, a handful of additions
+// each; runs of more than MSM_GIANT_SLOTS slots are re-queued for the block-per-run kernel.
+constexpr uint32_t MSM_GIANT_SLOTS = 256;
+template <class Fq>
+__global__ void __launch_bounds__(128)
+msm_stitch_long_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, const MsmLongRun* long_runs, const uint32_t* n_long,
+                       uint32_t long_cap, XYZZ<Fq>* buckets, MsmLongRun* giant_runs, uint32_t* n_giant) {
+  uint32_t count = *n_long;
+  if (count > long_cap) count = long_cap;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x) {
+    const MsmLongRun run = long_runs[r];
+    if (run.last - run.first > MSM_GIANT_SLOTS) {
+      giant_runs[atomicAdd(n_giant, 1u)] = run;  // at most `count` entries: same capacity as long_runs
+      continue;
+    }
+    XYZZ<Fq> acc = ld_words(part_pt + run.first);
+    for (uint32_t k = run.first + 1; k <= run.last; k++)
+      if (part_bkt[k] == run.bucket) g1_add(acc, ld_words(part_pt + k));
+    st_words(buckets + run.bucket, acc);
+  }
+}
+template <class Fq>
+__global__ void __launch_bounds__(128)
+msm_stitch_giant_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, const MsmLongRun* runs, const uint32_t* n_runs,
+                        XYZZ<Fq>* buckets) {
+  __shared__ uint4 sm_raw[128 * sizeof(XYZZ<Fq>) / 16];
+  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(sm_raw);
+  const uint32_t count = *n_runs;
+  for (uint32_t r = blockIdx.x; r < count; r += gridDim.x) {
+    const MsmLongRun run = runs[r];
+    XYZZ<Fq> acc = XYZZ<Fq>::inf();
+    for (uint32_t k = run.first + threadIdx.x; k <= run.last; k += 128)
+      if (part_bkt[k] == run.bucket) g1_add(acc, ld_words(part_pt + k));
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 64; s >= 1; s >>= 1) {
+      if ((int)threadIdx.x < s) {
+        XYZZ<Fq> t = sm[threadIdx.x];
+        g1_add(t, sm[threadIdx.x + s]);
+        sm[threadIdx.x] = t;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) st_words(buckets + run.bucket, sm[0]);
+    __syncthreads();
+  }
 }
 static __global__ void msm_total_kernel(const uint32_t* cursor, uint32_t B, uint32_t* total) { *total = cursor[B - 1]; }
 
@@ -450,7 +519,9 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
     const size_t max_threads = (max_refs + MSM_Q - 1) / MSM_Q + 256;  // launches round up to whole blocks
     DBuf<uint32_t> digits(cx, max_refs), hist(cx, B), offsets(cx, B), cursor(cx, B);
     DBuf<uint2> sorted(cx, max_refs);
-    DBuf<uint32_t> total(cx, 1), part_bkt(cx, 2 * max_threads);
+    DBuf<uint32_t> total(cx, 1), part_bkt(cx, 2 * max_threads), n_long(cx, 2);  // n_long[0]: long runs, [1]: giant runs
+    const uint32_t long_cap = 1u << 18;
+    DBuf<MsmLongRun> long_runs(cx, long_cap), giant_runs(cx, long_cap);
     DBuf<XYZZ<Fq>> part_pt(cx, 2 * max_threads);
     buckets.zero();  // empty buckets are never written: all-zero XYZZ is the point at infinity
     for (int j = 0; j < nj; j++) {
@@ -477,9 +548,18 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       cx.launches++;
       cx.span_end(sp);
       size_t nparts = 2 * (size_t)div_up(nthreads, 128) * 128;
-      msm_stitch_kernel<Fq><<<div_up(nparts, 128), 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, nparts, buckets.p + (size_t)j * B);
+      size_t sp1 = cx.span_begin("msm_stitch", (double)n);
+      n_long.zero();
+      (void)nparts;
+      msm_stitch_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, nthreads, offsets.p, cursor.p,
+                                                                           buckets.p + (size_t)j * B, long_runs.p, n_long.p, long_cap);
+      msm_stitch_long_kernel<Fq><<<2 * cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, long_runs.p, n_long.p, long_cap,
+                                                                         buckets.p + (size_t)j * B, giant_runs.p, n_long.p + 1);
+      msm_stitch_giant_kernel<Fq><<<2 * cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, giant_runs.p, n_long.p + 1,
+                                                                          buckets.p + (size_t)j * B);
       B2M_CHECK_LAUNCH();
-      cx.launches++;
+      cx.launches += 3;
+      cx.span_end(sp1);
     }
   }
   double units = 0;

@@ -165,3 +165,24 @@ def test_msm_large_trapdoor(b2m_ctx, log_n):
         assert util.srs_msm(srs, curve, 77, sc[:m]) == util.trapdoor_msm(curve, curve.g, beta, 77, sc[:m])
     finally:
         _lib.lib().b2m_srs_destroy(srs)
+
+
+def test_msm_skewed_scalars(b2m_ctx):
+    """Scalar distributions that put most references in a handful of buckets (a polynomial whose
+    coefficients are nearly all equal, as z_A of the reference's DummyCircuit is): exercises the
+    cut-bucket stitching, including the long-run path."""
+    curve = BLS12_381
+    r = curve.fr.p
+    n = 1 << 16
+    beta = 0x1b2c3d4e5f60718293a4b5c6d7e8f9 % r
+    powers = util.gpu_powers(b2m_ctx, curve, curve.g, beta, n)
+    srs = util.make_srs(b2m_ctx, curve, powers)
+    rnd = random.Random(21)
+    try:
+        v, w = rnd.randrange(r), rnd.randrange(r)
+        cases = [[v] * n, [v if i % 3 else w for i in range(n)], [v] * (n - 5) + [rnd.randrange(r) for _ in range(5)],
+                 [(i % 7) + 1 for i in range(n)], [r - 1 - (i % 2) for i in range(n)]]
+        for sc in cases:
+            assert util.srs_msm(srs, curve, 0, sc) == util.trapdoor_msm(curve, curve.g, beta, 0, sc)
+    finally:
+        _lib.lib().b2m_srs_destroy(srs)
