@@ -46,9 +46,8 @@ struct b2m_srs {
   size_t n_g, n_gamma;
   std::unique_ptr<b2m::Msm<b2m::FrBls, b2m::FqBls>> bls;
   std::unique_ptr<b2m::Msm<b2m::FrBn, b2m::FqBn>> bn;
-  // powers_of_gamma_g (hiding bases), device resident, raw bytes (Affine<Fq>[n_gamma]);
-  // gamma_idx[k] = the power of beta held in slot k.
-  void* gamma_dev = nullptr;
+  // gamma_idx[k] = the power of beta held in slot k of the powers_of_gamma_g (they live in the window
+  // tables right after the G1 powers: see Msm::n_extra)
   std::vector<uint64_t> gamma_idx;
 
   // slot of beta^i * gamma * G, or throws
@@ -66,22 +65,11 @@ struct b2m_srs {
     if (curve == B2M_CURVE_BLS12_381) {
       bls.reset(new Msm<FrBls, FqBls>(c->cx, reinterpret_cast<const Affine<FqBls>*>(g), ng, reinterpret_cast<const Affine<FqBls>*>(gamma), ngamma,
                                       window_bits));
-      if (ngamma) {
-        gamma_dev = c->cx.alloc_bytes(ngamma * sizeof(Affine<FqBls>));
-        B2M_CUDA(cudaMemcpyAsync(gamma_dev, gamma, ngamma * sizeof(Affine<FqBls>), cudaMemcpyHostToDevice, c->cx.stream));
-      }
     } else {
       bn.reset(new Msm<FrBn, FqBn>(c->cx, reinterpret_cast<const Affine<FqBn>*>(g), ng, reinterpret_cast<const Affine<FqBn>*>(gamma), ngamma,
                                   window_bits));
-      if (ngamma) {
-        gamma_dev = c->cx.alloc_bytes(ngamma * sizeof(Affine<FqBn>));
-        B2M_CUDA(cudaMemcpyAsync(gamma_dev, gamma, ngamma * sizeof(Affine<FqBn>), cudaMemcpyHostToDevice, c->cx.stream));
-      }
     }
     c->cx.sync();
-  }
-  ~b2m_srs() {
-    if (gamma_dev) ctx->cx.free_bytes(gamma_dev);
   }
   int window_bits() const { return bls ? bls->c : bn->c; }
 };

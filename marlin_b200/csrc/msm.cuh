@@ -62,8 +62,6 @@ struct Msm {
   // Several MSMs at once (the commitments of one prover round): bucket passes back to back, then ONE
   // batched log-depth reduction, so its latency is paid per round instead of per MSM.
   void run_batch(const MsmJob<Fr, Fq>* jobs, int nj);
-  // sum_i scalars[i] * bases[i] for a handful of terms (n <= 4096): hiding commitments.
-  void run_small(const Affine<Fq>* bases, const Fr* scalars, bool mont, int n, XYZZ<Fq>* out_xyzz);
   // Level-0 ABI bodies (include/b2m.h): host scalars in, host affine point out.
   void run_host(size_t base_off, const uint64_t* scalars, size_t n, uint64_t* out_xy, int* out_is_inf);
   static void g1_powers_host(Ctx& cx, const uint64_t* g_xy, const uint64_t* beta, size_t n, uint64_t* out);

@@ -125,10 +125,6 @@ static __global__ void msm_scatter_kernel(const uint32_t* digits, size_t n, size
 // current one is being added.
 constexpr int MSM_Q = 64;
 template <class Fq>
-struct MsmPartial {
-  XYZZ<Fq> pt;
-};
-template <class Fq>
 __global__ void __launch_bounds__(128)
 msm_accumulate_kernel(const Affine<Fq>* __restrict__ tables, size_t table_stride, const uint32_t* __restrict__ offsets,
                       const uint32_t* __restrict__ ends, const uint2* __restrict__ sorted, const uint32_t* __restrict__ total_refs_p, XYZZ<Fq>* __restrict__ buckets, XYZZ<Fq>* __restrict__ part_pt,
@@ -384,32 +380,6 @@ __global__ void __launch_bounds__(32) msm_combine_kernel(const XYZZ<Fq>* all, in
   if (jobs.j[j].out_affine) st_words(reinterpret_cast<Affine<Fq>*>(jobs.j[j].out_affine), g1_to_affine(total));
 }
 
-// ---- small MSM: one thread per term, double-and-add, block tree (n <= 256) -------------------
-template <class Fr, class Fq>
-__global__ void __launch_bounds__(256)
-msm_small_kernel(const Affine<Fq>* bases, const Fr* scalars, bool MONT, int n, XYZZ<Fq>* out) {
-  __shared__ uint4 sm_raw[256 * sizeof(XYZZ<Fq>) / 16];
-  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(sm_raw);
-  XYZZ<Fq> a = XYZZ<Fq>::inf();
-  for (int i = threadIdx.x; i < n; i += 256) {
-    Fr s = ld_fr(scalars + i);
-    if (MONT) s = s.to_canonical();
-    XYZZ<Fq> t = g1_scalar_mul<Fq>(ld_affine(bases + i), s.l, Fr::N);
-    g1_add(a, t);
-  }
-  sm[threadIdx.x] = a;
-  __syncthreads();
-  for (int s = 128; s >= 1; s >>= 1) {
-    if ((int)threadIdx.x < s) {
-      XYZZ<Fq> t = sm[threadIdx.x];
-      g1_add(t, sm[threadIdx.x + s]);
-      sm[threadIdx.x] = t;
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) st_words(out, sm[0]);
-}
-
 // out[i] = beta^i * g  (test-SRS generation; the G1 half of KZG10::setup)
 template <class Fr, class Fq>
 __global__ void g1_powers_kernel(Affine<Fq> g, Fr beta, size_t n, Affine<Fq>* out) {
@@ -606,14 +576,6 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
   cx.span_end(sp2);
   exchange();
   // the DBufs are stream-ordered: their frees are enqueued behind the kernels above
-}
-
-template <class Fr, class Fq>
-void Msm<Fr, Fq>::run_small(const Affine<Fq>* bases, const Fr* scalars, bool mont, int n, XYZZ<Fq>* out_xyzz) {
-  B2M_REQUIRE(n >= 0 && n <= 4096, B2M_ERR_INVALID_ARG, "run_small: n = %d", n);
-  msm_small_kernel<Fr, Fq><<<1, 256, 0, ctx->stream>>>(bases, scalars, mont, n, out_xyzz);
-  B2M_CHECK_LAUNCH();
-  ctx->launches++;
 }
 
 template <class Fr, class Fq>

@@ -20,7 +20,6 @@
 namespace b2m {
 
 constexpr int NTT_MAX_K = 8;     // stages per pass
-constexpr int NTT_COLS = 8;      // contiguous columns per tile
 constexpr int NTT_THREADS = 256;
 
 template <class Fr>
