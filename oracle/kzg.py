@@ -52,13 +52,24 @@ class UniversalParams:
         self.g = g
         self.gamma = gamma % curve.fr.p
         self.gamma_g = ec.scalar_mul(curve, gamma, g)
-        self.powers_of_g = powers_of_g if powers_of_g is not None else ec.fixed_base_powers(curve, g, beta, max_degree + 1)
+        if powers_of_g == "lazy":  # verifier-only use: individual powers on demand, O(1) each through the trapdoor
+            self.powers_of_g = _LazyPowers(curve, g, self.beta)
+        else:
+            self.powers_of_g = powers_of_g if powers_of_g is not None else ec.fixed_base_powers(curve, g, beta, max_degree + 1)
         self._gamma_cache = {}
 
     def power_of_gamma_g(self, i):
         if i not in self._gamma_cache:
             self._gamma_cache[i] = ec.scalar_mul(self.curve, pow(self.beta, i, self.curve.fr.p), self.gamma_g)
         return self._gamma_cache[i]
+
+
+class _LazyPowers:
+    def __init__(self, curve, g, beta):
+        self.curve, self.g, self.beta = curve, g, beta
+
+    def __getitem__(self, i):
+        return ec.scalar_mul(self.curve, pow(self.beta, i, self.curve.fr.p), self.g)
 
 
 class CommitterKey:

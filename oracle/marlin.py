@@ -195,3 +195,97 @@ def serialize_proof(curve, scheme, proof):
         out += b"\x00" if rv is None else b"\x01" + rv.to_bytes(f.nbytes, "little")
     out += b"\x00"  # BatchLCProof.evals = None
     return out
+
+
+# ---- CanonicalDeserialize + verification from public data only ------------------------------------------------
+def _g1_decompress(curve, data):
+    """Inverse of transcript.g1_compressed (ark-serialize SWFlags): x little-endian, bit 7 = y is the larger root,
+    bit 6 = infinity.  y = sqrt(x^3 + b) via exponent (p + 1) / 4 (both base fields are 3 mod 4)."""
+    fq = curve.fq
+    b = bytearray(data)
+    flags = b[-1] & 0xc0
+    b[-1] &= 0x3f
+    if flags & 0x40:
+        return None
+    x = int.from_bytes(bytes(b), "little")
+    p = fq.p
+    assert p % 4 == 3
+    rhs = (x * x * x + curve.b) % p
+    y = pow(rhs, (p + 1) // 4, p)
+    if y * y % p != rhs:
+        raise ValueError("compressed point is not on the curve")
+    larger = y > (p - y) % p
+    if bool(flags & 0x80) != larger:
+        y = (p - y) % p
+    return (x, y)
+
+
+def deserialize_proof(curve, scheme, data):
+    """`Proof::deserialize` (CanonicalDeserialize) for the layout serialize_proof writes."""
+    f = curve.fr
+    nq = curve.fq.nbytes
+    off = 0
+
+    def u64():
+        nonlocal off
+        v = struct.unpack_from("<Q", data, off)[0]
+        off += 8
+        return v
+
+    def point():
+        nonlocal off
+        P = _g1_decompress(curve, data[off:off + nq])
+        off += nq
+        return P
+
+    def byte():
+        nonlocal off
+        v = data[off]
+        off += 1
+        return v
+
+    commitments = []
+    for _ in range(u64()):
+        rnd = []
+        for _ in range(u64()):
+            c = point()
+            sh = None
+            if scheme == kzg.MARLIN and byte():
+                sh = point()
+            rnd.append(kzg.Commitment(c, sh))
+        commitments.append(rnd)
+    evaluations = []
+    for _ in range(u64()):
+        evaluations.append(int.from_bytes(data[off:off + f.nbytes], "little"))
+        off += f.nbytes
+    for _ in range(u64()):
+        assert byte() == 0  # ProverMsg::EmptyMessage
+    pc_proof = []
+    for _ in range(u64()):
+        w = point()
+        rv = None
+        if byte():
+            rv = int.from_bytes(data[off:off + f.nbytes], "little")
+            off += f.nbytes
+        pc_proof.append((w, rv))
+    assert byte() == 0 and off == len(data)
+    return Proof(commitments, evaluations, pc_proof)
+
+
+def verifier_key_from_public(curve, scheme, srs, num_constraints, num_variables, num_non_zero, index_comms):
+    """What `Marlin::verify` needs, built from public data only: index_info, the six index commitments and the
+    (trimmed) SRS.  `srs` is a kzg.UniversalParams (the trapdoor replaces the pairing, see kzg.py)."""
+    f = curve.fr
+    pk = IndexProverKey()
+    pk.curve, pk.scheme = curve, scheme
+
+    class _Idx:
+        pass
+
+    pk.index = _Idx()
+    pk.index.info = ahp.IndexInfo(num_variables, num_constraints, num_non_zero, None)
+    md = ahp.max_degree(f, num_constraints, num_variables, num_non_zero)
+    pk.ck = kzg.CommitterKey(srs, md, 1, ahp.get_degree_bounds(f, pk.index.info), scheme)
+    pk.index_comms = [kzg.Commitment(c, None) for c in index_comms]
+    pk.vk_bytes = index_vk_bytes(curve, scheme, pk.index.info, pk.index_comms)
+    return pk

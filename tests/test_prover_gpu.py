@@ -185,3 +185,42 @@ def test_golden_fixture_bytes(gctx, case):
             pk.close()
     finally:
         srs.close()
+
+
+@pytest.mark.parametrize("curve_name,log_n,scheme", [("bls12_381", 16, "marlin_kzg10"), ("bls12_381", 16, "sonic_kzg10"),
+                                                     ("bn254", 16, "marlin_kzg10"), ("bls12_381", 20, "marlin_kzg10")])
+def test_full_size_proof_verifies(gctx, curve_name, log_n, scheme):
+    """Size-independent check at BASELINE.json's sizes (the oracle cannot *prove* 2^20 in reasonable time, but
+    verification needs only public data): the GPU proof of a 2^log_n-constraint DummyCircuit is accepted by the
+    oracle's restatement of `Marlin::verify` for the right public input and rejected for a wrong one or after a
+    one-byte change [reference src/test.rs:158-161]."""
+    from oracle import ec
+    from oracle.params import CURVES
+    curve = CURVES[curve_name]
+    f = curve.fr
+    n = 1 << log_n
+    a, b = 0x1234567890abcdef1234567890abcdef, 0xfedcba0987654321fedcba0987654321
+    beta, gamma = 0x5eed5eed5eed5eed5eed5eed, 7
+    m = api.Marlin(curve_name, scheme, ctx=gctx)
+    srs = m.universal_setup(n, n, 3 * n, beta=beta, gamma=gamma, degree_bounds=(n - 2, 4 * n - 2))
+    circ = gr1cs.dummy_circuit(m.curve_id, a, b, 10, n)
+    try:
+        pk = m.index(srs, circ)
+        try:
+            proof_bytes = m.prove(pk, circ, api.ZkRng())
+            comms = util.points_from_limbs(curve, pk.index_comms)
+            lazy = kzg.UniversalParams(curve, srs.max_degree, beta, curve.g, gamma, powers_of_g="lazy")
+            vk = omarlin.verifier_key_from_public(curve, SCHEMES[scheme], lazy, n, n, 3 * (n - 1), comms)
+            assert vk.vk_bytes == pk.vk_bytes
+            proof = omarlin.deserialize_proof(curve, SCHEMES[scheme], proof_bytes)
+            assert all(ec.on_curve(curve, c.comm) for rnd in proof.commitments for c in rnd)
+            c_pub = a * b % f.p
+            assert omarlin.verify(vk, [c_pub], proof)
+            assert not omarlin.verify(vk, [(c_pub + 1) % f.p], proof)
+            bad = omarlin.deserialize_proof(curve, SCHEMES[scheme], proof_bytes)
+            bad.evaluations[2] = (bad.evaluations[2] + 1) % f.p
+            assert not omarlin.verify(vk, [c_pub], bad)
+        finally:
+            pk.close()
+    finally:
+        srs.close()
