@@ -110,6 +110,32 @@ int b2m_srs_msm(b2m_srs* srs, size_t base_off, const uint64_t* scalars, size_t n
 int b2m_g1_powers(b2m_ctx* ctx, int curve, const uint64_t* g_xy, const uint64_t* beta, size_t n,
                   uint64_t* out_powers_xy);
 
+/* The caller's `zk_rng: &mut R` (reference src/lib.rs:154).  A ChaCha block RNG is described by
+ * its key and word position so the mask polynomial (3|H| draws, src/ahp/prover.rs:371) can
+ * be sampled on the device bit-exactly; word_pos is updated to the position after the call. */
+typedef struct {
+  int kind;          /* B2M_RNG_CHACHA* */
+  uint8_t key[32];
+  uint64_t word_pos; /* number of 32-bit words already consumed from the stream */
+} b2m_rng;
+
+/* ---- Level 1: polynomial-commitment ABI --------------------------------------------------------- */
+
+/* Replaces `PC::commit(ck, polynomials, rng)` for PC = MarlinKZG10 / SonicKZG10 [U ark-poly-commit 0.3
+ * marlin_pc/mod.rs, sonic_pc/mod.rs commit -> kzg10::KZG10::commit]; call sites reference
+ * src/lib.rs:125,172,193,213.  Polynomials are host coefficient arrays (Montgomery Fr, low degree first)
+ * committed in order with the blinding polynomials drawn from `rng` exactly as the reference does
+ * (hiding_bound h draws h + 2 coefficients; MarlinKZG10 draws a second set for the shifted commitment).
+ *   degree_bounds[i] / hiding_bounds[i] : -1 for None.
+ *   out_comm_xy[i]      affine commitment; out_shifted_xy[i]: MarlinKZG10 shifted commitment of a bounded
+ *                        polynomial (all-zero when absent; unused for SonicKZG10).
+ *   out_rand / out_shifted_rand : blinding polynomial coefficients, rand_stride Fr per polynomial (zero padded).
+ * rng may be NULL when no polynomial is hiding (B2M_ERR_MISSING_RNG otherwise). */
+int b2m_pc_commit(b2m_srs* srs, int pc_variant, size_t n_polys, const uint64_t* const* coeffs,
+                  const size_t* n_coeffs, const int64_t* degree_bounds, const int64_t* hiding_bounds,
+                  b2m_rng* rng, uint64_t* out_comm_xy, uint64_t* out_shifted_xy, uint64_t* out_rand,
+                  uint64_t* out_shifted_rand, size_t rand_stride);
+
 /* ---- Level 2: prover ABI ---------------------------------------------------------------- */
 
 /* R1CS matrix in CSR form, as `ConstraintSystem::to_matrices()` yields it
@@ -135,14 +161,6 @@ int b2m_index_vk_bytes(const b2m_index* idx, uint8_t* out, size_t cap, size_t* l
 /* Commitments to the index polynomials (affine x||y Montgomery, 6 points). */
 int b2m_index_comms(const b2m_index* idx, uint64_t* out_xy);
 
-/* The caller's `zk_rng: &mut R` (reference src/lib.rs:154).  A ChaCha block RNG is described by
- * its key and word position so the mask polynomial (3|H| draws, src/ahp/prover.rs:371) can
- * be sampled on the device bit-exactly; word_pos is updated to the position after the call. */
-typedef struct {
-  int kind;          /* B2M_RNG_CHACHA* */
-  uint8_t key[32];
-  uint64_t word_pos; /* number of 32-bit words already consumed from the stream */
-} b2m_rng;
 
 /* Replaces `Marlin::prove` (reference src/lib.rs:151-311).  formatted_input: the instance
  * assignment including the leading one (|X| elements); witness: the witness assignment

@@ -158,6 +158,28 @@ class Marlin:
                                     _lib.ptr(gi), len(gi), window_bits, ctypes.byref(h)))
         return UniversalSRS(self.ctx, self.curve_id, h, len(powers_limbs) - 1, powers_limbs)
 
+    # -- PC::commit (Level 1) ------------------------------------------------------------------------------
+    def commit(self, srs, polys, zk_rng=None):
+        """`PC::commit(ck, polynomials, rng)` [reference src/lib.rs:125,172,193,213].  polys: list of
+        (coeff_limbs uint64[n,4] Montgomery, degree_bound or None, hiding_bound or None).
+        Returns (comms, shifted_comms, rands, shifted_rands) as limb arrays; rands are 4 Fr per polynomial."""
+        L = _lib.lib()
+        n = len(polys)
+        lq = _lib.LIMBS[self.curve_id][1]
+        arrs = [np.ascontiguousarray(p[0], dtype=np.uint64) for p in polys]
+        ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        lens = (ctypes.c_size_t * n)(*[len(a) for a in arrs])
+        db = (ctypes.c_int64 * n)(*[-1 if p[1] is None else p[1] for p in polys])
+        hb = (ctypes.c_int64 * n)(*[-1 if p[2] is None else p[2] for p in polys])
+        comm = np.zeros((n, 2 * lq), dtype=np.uint64)
+        shifted = np.zeros((n, 2 * lq), dtype=np.uint64)
+        rand = np.zeros((n, 4, 4), dtype=np.uint64)
+        srand = np.zeros((n, 4, 4), dtype=np.uint64)
+        rp = ctypes.byref(zk_rng.c) if zk_rng is not None else None
+        _lib.check(L.b2m_pc_commit(srs.handle, self.pc, n, ptrs, lens, db, hb, rp, _lib.ptr(comm), _lib.ptr(shifted), _lib.ptr(rand),
+                                   _lib.ptr(srand), 4))
+        return comm, shifted, rand, srand
+
     # -- index -----------------------------------------------------------------------------------------
     def index(self, srs, r1cs):
         """[reference src/lib.rs:100-148] -> IndexProverKey (device resident); .vk_bytes is `index_vk` (ToBytes)."""

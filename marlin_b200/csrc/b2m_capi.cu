@@ -138,6 +138,27 @@ int b2m_g1_powers(b2m_ctx* ctx, int curve, const uint64_t* g_xy, const uint64_t*
   });
 }
 
+// ---- Level 1 ----------------------------------------------------------------------------------
+int b2m_pc_commit(b2m_srs* srs, int pc_variant, size_t n_polys, const uint64_t* const* coeffs, const size_t* n_coeffs,
+                  const int64_t* degree_bounds, const int64_t* hiding_bounds, b2m_rng* rng, uint64_t* out_comm_xy,
+                  uint64_t* out_shifted_xy, uint64_t* out_rand, uint64_t* out_shifted_rand, size_t rand_stride) {
+  return guard([&] {
+    B2M_REQUIRE(srs && coeffs && n_coeffs && degree_bounds && hiding_bounds && out_comm_xy && out_rand, B2M_ERR_INVALID_ARG, "null argument");
+    B2M_REQUIRE(pc_variant == B2M_PC_MARLIN_KZG10 || pc_variant == B2M_PC_SONIC_KZG10, B2M_ERR_INVALID_ARG, "unknown PC variant");
+    B2M_REQUIRE(pc_variant != B2M_PC_MARLIN_KZG10 || (out_shifted_xy && out_shifted_rand), B2M_ERR_INVALID_ARG,
+                "MarlinKZG10 needs the shifted output buffers");
+    B2M_REQUIRE(rng == nullptr || rng->kind == B2M_RNG_CHACHA8 || rng->kind == B2M_RNG_CHACHA12 || rng->kind == B2M_RNG_CHACHA20,
+                B2M_ERR_MISSING_RNG, "unsupported rng kind");
+    srs->ctx->cx.use();
+    if (srs->curve == B2M_CURVE_BLS12_381)
+      pc_commit_bls(srs, pc_variant, n_polys, coeffs, n_coeffs, degree_bounds, hiding_bounds, rng, out_comm_xy, out_shifted_xy, out_rand,
+                    out_shifted_rand, rand_stride);
+    else
+      pc_commit_bn(srs, pc_variant, n_polys, coeffs, n_coeffs, degree_bounds, hiding_bounds, rng, out_comm_xy, out_shifted_xy, out_rand,
+                   out_shifted_rand, rand_stride);
+  });
+}
+
 // ---- Level 2 ----------------------------------------------------------------------------------
 struct b2m_index {
   b2m_srs* srs;

@@ -6,4 +6,10 @@ IndexBase* make_index_bls(b2m_srs* srs, int pc, size_t nc, size_t nv, size_t ni,
   idx->build(a, b, c);
   return idx.release();
 }
+void pc_commit_bls(b2m_srs* srs, int pc, size_t n_polys, const uint64_t* const* coeffs, const size_t* n_coeffs,
+                   const int64_t* degree_bounds, const int64_t* hiding_bounds, b2m_rng* rng, uint64_t* out_comm_xy, uint64_t* out_shifted_xy,
+                   uint64_t* out_rand, uint64_t* out_shifted_rand, size_t rand_stride) {
+  pc_commit_impl<FrBls, FqBls>(srs, *srs->bls, pc, n_polys, coeffs, n_coeffs, degree_bounds, hiding_bounds, rng, out_comm_xy, out_shifted_xy, out_rand,
+                             out_shifted_rand, rand_stride);
+}
 }  // namespace b2m

@@ -26,6 +26,7 @@ namespace b2m {
 constexpr int MSM_MIN_WINDOW = 8;  // 5 window-id bits in a reference: ceil(256 / c) <= 32
 constexpr int MSM_IDX_BITS = 26;  // point index bits in a sorted reference
 constexpr uint32_t MSM_NO_DIGIT = 0xffffffffu;
+constexpr int MSM_MAX_BATCH = 8;   // MSMs per run_batch call
 
 template <class Fr, class Fq>
 struct MsmJob {

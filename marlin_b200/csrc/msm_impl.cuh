@@ -327,7 +327,6 @@ struct MsmFinishJob {
   void* out_xyzz;     // XYZZ* or null
   void* out_affine;   // Affine* or null
 };
-constexpr int MSM_MAX_BATCH = 8;
 struct MsmFinishJobs {
   MsmFinishJob j[MSM_MAX_BATCH];
 };

@@ -905,4 +905,75 @@ struct MarlinIndex : IndexBase {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------
+// Level 1: `PC::commit` over host polynomials [U ark-poly-commit marlin_pc / sonic_pc commit]
+// ---------------------------------------------------------------------------------------------------
+template <class Fr, class Fq>
+void pc_commit_impl(b2m_srs* srs, Msm<Fr, Fq>& msm, int pc, size_t n_polys, const uint64_t* const* coeffs, const size_t* n_coeffs,
+                    const int64_t* degree_bounds, const int64_t* hiding_bounds, b2m_rng* rng, uint64_t* out_comm_xy,
+                    uint64_t* out_shifted_xy, uint64_t* out_rand, uint64_t* out_shifted_rand, size_t rand_stride) {
+  using Pt = Affine<Fq>;
+  Ctx& cx = srs->ctx->cx;
+  const size_t D = srs->n_g - 1;
+  const bool marlin = pc == B2M_PC_MARLIN_KZG10;
+  bool any_hiding = false;
+  for (size_t i = 0; i < n_polys; i++) any_hiding = any_hiding || hiding_bounds[i] >= 0;
+  B2M_REQUIRE(!any_hiding || rng != nullptr, B2M_ERR_MISSING_RNG, "a hiding bound was requested but rng is null");
+  ChaChaHost zk;
+  if (rng) zk = ChaChaHost(rng->key, rng->kind, rng->word_pos);
+  std::vector<DBuf<Fr>> polys, blind;
+  std::vector<MsmJob<Fr, Fq>> jobs;
+  DBuf<Pt> out(cx, 2 * n_polys);
+  B2M_CUDA(cudaMemsetAsync(out.p, 0, 2 * n_polys * sizeof(Pt), cx.stream));
+  memset(out_rand, 0, n_polys * rand_stride * sizeof(Fr));
+  if (out_shifted_rand) memset(out_shifted_rand, 0, n_polys * rand_stride * sizeof(Fr));
+  auto draw = [&](int64_t hb, uint64_t* dst) -> std::vector<Fr> {
+    std::vector<Fr> r;
+    if (hb < 0) return r;
+    B2M_REQUIRE((size_t)hb + 2 <= rand_stride, B2M_ERR_INVALID_ARG, "rand_stride %zu < hiding bound %lld + 2", rand_stride, (long long)hb);
+    for (int64_t k = 0; k < hb + 2; k++) r.push_back(field_rand<Fr>(zk));  // Randomness::rand: degree hiding_bound + 1
+    memcpy(dst, r.data(), r.size() * sizeof(Fr));
+    return r;
+  };
+  auto job = [&](const Fr* dev, size_t len, size_t off, const std::vector<Fr>& b, size_t gslot, Pt* dst) {
+    const Fr* s2 = nullptr;
+    if (!b.empty()) {
+      blind.emplace_back(cx, b.size());
+      blind.back().upload(b.data(), b.size());
+      s2 = blind.back().p;
+      for (size_t k = 1; k < b.size(); k++)
+        B2M_REQUIRE(srs->gamma_slot(srs->gamma_idx[gslot] + k) == gslot + k, B2M_ERR_INVALID_ARG, "gamma powers are not consecutive");
+    }
+    jobs.push_back(MsmJob<Fr, Fq>{dev, true, len, off, s2, b.size(), gslot, nullptr, 0, nullptr, dst});
+  };
+  for (size_t i = 0; i < n_polys; i++) {
+    const size_t len = n_coeffs[i];
+    B2M_REQUIRE(len <= srs->n_g, B2M_ERR_DEGREE_TOO_LARGE, "polynomial %zu has %zu coefficients, the SRS %zu powers", i, len, srs->n_g);
+    polys.emplace_back(cx, len ? len : 1);
+    if (len) polys.back().upload(reinterpret_cast<const Fr*>(coeffs[i]), len);
+    const int64_t d = degree_bounds[i], hb = hiding_bounds[i];
+    if (d >= 0) {
+      B2M_REQUIRE((size_t)d <= D && len <= (size_t)d + 1, B2M_ERR_DEGREE_TOO_LARGE, "polynomial %zu exceeds its degree bound %lld", i, (long long)d);
+    }
+    if (marlin) {
+      job(polys.back().p, len, 0, draw(hb, out_rand + 4 * rand_stride * i), hb >= 0 ? srs->gamma_slot(0) : 0, out.p + 2 * i);
+      if (d >= 0)
+        job(polys.back().p, len, D - (size_t)d, draw(hb, out_shifted_rand + 4 * rand_stride * i), hb >= 0 ? srs->gamma_slot(0) : 0,
+            out.p + 2 * i + 1);
+    } else {
+      if (d >= 0) job(polys.back().p, len, D - (size_t)d, draw(hb, out_rand + 4 * rand_stride * i), hb >= 0 ? srs->gamma_slot(D - (size_t)d) : 0, out.p + 2 * i);
+      else job(polys.back().p, len, 0, draw(hb, out_rand + 4 * rand_stride * i), hb >= 0 ? srs->gamma_slot(0) : 0, out.p + 2 * i);
+    }
+  }
+  for (size_t at = 0; at < jobs.size(); at += MSM_MAX_BATCH)
+    msm.run_batch(jobs.data() + at, (int)std::min<size_t>(MSM_MAX_BATCH, jobs.size() - at));
+  std::vector<Pt> h(2 * n_polys);
+  out.download(h.data(), h.size());
+  for (size_t i = 0; i < n_polys; i++) {
+    memcpy(out_comm_xy + i * (2 * Fq::N / 2), &h[2 * i], sizeof(Pt));
+    if (out_shifted_xy) memcpy(out_shifted_xy + i * (2 * Fq::N / 2), &h[2 * i + 1], sizeof(Pt));
+  }
+  if (rng) rng->word_pos = zk.word_pos;
+}
+
 }  // namespace b2m

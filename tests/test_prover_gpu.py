@@ -224,3 +224,49 @@ def test_full_size_proof_verifies(gctx, curve_name, log_n, scheme):
             pk.close()
     finally:
         srs.close()
+
+
+@pytest.mark.parametrize("scheme", list(SCHEMES))
+def test_pc_commit_level1(gctx, scheme):
+    """Level-1 ABI (b2m_pc_commit) against the oracle's `PC::commit`: same commitments, same blinding polynomials,
+    same RNG consumption, for unbounded / bounded / hiding / non-hiding polynomials in one call."""
+    import random
+    curve = BLS12_381
+    f = curve.fr
+    rnd = random.Random(17)
+    D = 63
+    osrs = kzg.UniversalParams(curve, D, 0xabcdef, ec_scalar(curve, 3), 11)
+    bounds = [10, 40]
+    ck = kzg.CommitterKey(osrs, D, 1, bounds, SCHEMES[scheme])
+    polys = [kzg.LabeledPoly("a", [rnd.randrange(f.p) for _ in range(20)], None, 1),
+             kzg.LabeledPoly("b", [rnd.randrange(f.p) for _ in range(11)], 10, 1),
+             kzg.LabeledPoly("c", [0, 0, 5] + [rnd.randrange(f.p) for _ in range(30)], 40, None),
+             kzg.LabeledPoly("d", [rnd.randrange(f.p) for _ in range(64)], None, None),
+             kzg.LabeledPoly("e", [7], None, 1)]
+    zk = orng.ChaChaRng(bytes(range(32)), 12)
+    ocomms, orands = kzg.commit(kzg.Engine(False), ck, polys, zk)
+    m = api.Marlin("bls12_381", scheme, ctx=gctx)
+    gidx = sorted({0, 1, 2} | ({D - d + i for d in bounds for i in range(3)} if scheme == "sonic_kzg10" else set()))
+    srs = m.srs_from_points(util.points_to_limbs(curve, osrs.powers_of_g), util.points_to_limbs(curve, [osrs.power_of_gamma_g(i) for i in gidx]), gidx)
+    try:
+        grng = api.ZkRng(bytes(range(32)), 12)
+        comm, shifted, rand, srand = m.commit(srs, [(util.fr_to_mont_limbs(curve, p.coeffs), p.degree_bound, p.hiding_bound) for p in polys], grng)
+        assert grng.word_pos == zk.word_pos
+        assert util.points_from_limbs(curve, comm) == [c.comm for c in ocomms]
+        for i, (c, r) in enumerate(zip(ocomms, orands)):
+            assert util.fr_from_mont_limbs(curve, rand[i])[:len(r.rand)] == r.rand
+            if scheme == "marlin_kzg10":
+                assert util.points_from_limbs(curve, shifted[i:i + 1])[0] == c.shifted
+                if r.shifted_rand:
+                    assert util.fr_from_mont_limbs(curve, srand[i])[:len(r.shifted_rand)] == r.shifted_rand
+        from marlin_b200 import _lib
+        with pytest.raises(_lib.B2MError) as e:
+            m.commit(srs, [(util.fr_to_mont_limbs(curve, [1, 2, 3]), None, 1)], None)
+        assert e.value.code == 7  # B2M_ERR_MISSING_RNG
+    finally:
+        srs.close()
+
+
+def ec_scalar(curve, k):
+    from oracle import ec
+    return ec.scalar_mul(curve, k, curve.g)
