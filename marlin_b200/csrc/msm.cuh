@@ -50,6 +50,7 @@ struct Msm {
   size_t n_extra = 0;  // further fixed bases (powers_of_gamma_g) appended after them
   size_t stride = 0;   // n_srs + n_extra: entries per window table
   int c = 0, W = 0;
+  int acc_ctas_per_sm = 3;  // resident CTAs of msm_accumulate_kernel per SM (occupancy query)
   DBuf<Affine<Fq>> tables;  // [W][stride]:  tables[w * stride + i] = 2^(c*w) * P_i
 
   static int pick_window(size_t n);

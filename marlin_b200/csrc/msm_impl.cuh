@@ -123,20 +123,22 @@ static __global__ void msm_scatter_kernel(const uint32_t* digits, size_t n, size
 // is stored straight into buckets[b]; the (at most two) runs per thread that cut a bucket are stored
 // as partials and stitched together by msm_stitch_kernel.  The next point is prefetched while the
 // current one is being added.
-constexpr int MSM_Q = 64;
+constexpr int MSM_Q = 64;      // nominal references per thread; the launch picks q near it so the grid is whole waves
+constexpr int MSM_Q_MIN = 32;  // buffers are sized for at least this many references per thread
 template <class Fq>
 __global__ void __launch_bounds__(128)
 msm_accumulate_kernel(const Affine<Fq>* __restrict__ tables, size_t table_stride, const uint32_t* __restrict__ offsets,
-                      const uint32_t* __restrict__ ends, const uint2* __restrict__ sorted, const uint32_t* __restrict__ total_refs_p, XYZZ<Fq>* __restrict__ buckets, XYZZ<Fq>* __restrict__ part_pt,
+                      const uint32_t* __restrict__ ends, const uint2* __restrict__ sorted, const uint32_t* __restrict__ total_refs_p,
+                      const uint32_t q, XYZZ<Fq>* __restrict__ buckets, XYZZ<Fq>* __restrict__ part_pt,
                       uint32_t* __restrict__ part_bkt) {
   const uint32_t total = *total_refs_p;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t start64 = (uint64_t)t * MSM_Q;
+  const uint64_t start64 = (uint64_t)t * q;
   // partial slots 2t (head) and 2t+1 (tail) default to "none"
   uint32_t head_b = MSM_NO_DIGIT, tail_b = MSM_NO_DIGIT;
   if (start64 < total) {
     const uint32_t start = (uint32_t)start64;
-    const uint32_t end = (total - start > (uint32_t)MSM_Q) ? start + MSM_Q : total;
+    const uint32_t end = (total - start > q) ? start + q : total;
     uint2 rb = __ldg(sorted + start);
     uint32_t ref = rb.x;
     uint32_t cur_b = rb.y;
@@ -184,8 +186,8 @@ struct MsmLongRun {
 };
 template <class Fq>
 __global__ void __launch_bounds__(128)
-msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nthreads, const uint32_t* offsets, const uint32_t* ends,
-                  XYZZ<Fq>* buckets, MsmLongRun* long_runs, uint32_t* n_long, uint32_t long_cap) {
+msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nthreads, const uint32_t q, const uint32_t* offsets,
+                  const uint32_t* ends, XYZZ<Fq>* buckets, MsmLongRun* long_runs, uint32_t* n_long, uint32_t long_cap) {
   // One thread per accumulate-thread u.  A run of partials starts either in u's tail slot (a bucket that
   // begins inside u's range and continues into u + 1) or in u's head slot when the bucket begins exactly at
   // u's first reference; u can hold only one of the two.  The common run is the pair (tail of u, head of
@@ -197,9 +199,9 @@ msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nthr
   if (b == MSM_NO_DIGIT) {
     first = 2u * (uint32_t)u;
     b = part_bkt[first];
-    if (b == MSM_NO_DIGIT || offsets[b] != (uint32_t)u * (uint32_t)MSM_Q) return;  // not a run start
+    if (b == MSM_NO_DIGIT || offsets[b] != (uint32_t)u * q) return;  // not a run start
   }
-  const uint32_t t1 = (ends[b] - 1u) / (uint32_t)MSM_Q;  // thread holding the bucket's last reference
+  const uint32_t t1 = (ends[b] - 1u) / q;  // thread holding the bucket's last reference
   const uint32_t last = 2u * t1;                          // its head slot closes the run
   if (t1 > (uint32_t)u + 1u) {
     uint32_t slot = atomicAdd(n_long, 1u);
@@ -414,6 +416,8 @@ Msm<Fr, Fq>::Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, const Affine<
   B2M_CHECK_LAUNCH();
   cx.launches++;
   cx.sync();
+  B2M_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas_per_sm, msm_accumulate_kernel<Fq>, 128, 0));
+  if (acc_ctas_per_sm < 1) acc_ctas_per_sm = 1;
 }
 
 template <class Fr, class Fq>
@@ -485,7 +489,7 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
   {
     // sort + accumulate, one job after the other (both saturate the chip)
     const size_t max_refs = (size_t)W * max_n;
-    const size_t max_threads = (max_refs + MSM_Q - 1) / MSM_Q + 256;  // launches round up to whole blocks
+    const size_t max_threads = (max_refs + MSM_Q_MIN - 1) / MSM_Q_MIN + 256;  // launches round up to whole blocks
     DBuf<uint32_t> digits(cx, max_refs), hist(cx, B), offsets(cx, B), cursor(cx, B);
     DBuf<uint2> sorted(cx, max_refs);
     DBuf<uint32_t> total(cx, 1), part_bkt(cx, 2 * max_threads), n_long(cx, 2);  // n_long[0]: long runs, [1]: giant runs
@@ -510,8 +514,16 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       cx.launches += 3;
       cx.span_end(sp0);
       size_t sp = cx.span_begin("msm_accumulate_kernel", (double)n);
-      const size_t nthreads = ((size_t)W * nt + MSM_Q - 1) / MSM_Q;  // upper bound on ceil(total_refs / Q)
-      msm_accumulate_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(tables.p, stride, offsets.p, cursor.p, sorted.p, total.p,
+      // References per thread: near MSM_Q, chosen so that the grid is a whole number of waves of
+      // (SMs x resident CTAs) -- every thread does the same work, so a partial last wave is pure loss.
+      const size_t refs = (size_t)W * nt;  // upper bound on the reference count (zero digits are rare)
+      const size_t wave = (size_t)cx.sm_count * acc_ctas_per_sm * 128;
+      size_t waves = (refs + wave * MSM_Q / 2) / (wave * MSM_Q);
+      if (waves < 1) waves = 1;
+      uint32_t q = (uint32_t)((refs + waves * wave - 1) / (waves * wave));
+      if (q < (uint32_t)MSM_Q_MIN) q = MSM_Q_MIN;
+      const size_t nthreads = (refs + q - 1) / q;
+      msm_accumulate_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(tables.p, stride, offsets.p, cursor.p, sorted.p, total.p, q,
                                                                                buckets.p + (size_t)j * B, part_pt.p, part_bkt.p);
       B2M_CHECK_LAUNCH();
       cx.launches++;
@@ -520,7 +532,7 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       size_t sp1 = cx.span_begin("msm_stitch", (double)n);
       n_long.zero();
       (void)nparts;
-      msm_stitch_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, nthreads, offsets.p, cursor.p,
+      msm_stitch_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, nthreads, q, offsets.p, cursor.p,
                                                                            buckets.p + (size_t)j * B, long_runs.p, n_long.p, long_cap);
       msm_stitch_long_kernel<Fq><<<2 * cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, long_runs.p, n_long.p, long_cap,
                                                                          buckets.p + (size_t)j * B, giant_runs.p, n_long.p + 1);
