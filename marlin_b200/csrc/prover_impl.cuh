@@ -387,6 +387,7 @@ struct MarlinIndex : IndexBase {
   void commit_round(std::vector<Oracle*>& polys, ChaChaHost& zk) {
     std::vector<DBuf<Fr>> keep_sc;
     DBuf<Pt> out(cx, 2 * polys.size());
+    out.zero();  // the shifted slot of an unbounded polynomial is never written
     std::vector<MsmJob<Fr, Fq>> jobs;
     for (size_t i = 0; i < polys.size(); i++) {
       Oracle& o = *polys[i];
