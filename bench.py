@@ -220,6 +220,14 @@ def main():
     acc = kern.get("msm_accumulate_kernel", {"ms": 0.0, "units": 0.0, "launches": 0})
     pair_bytes = 128 if args.curve == "bls12_381" else 96
     achieved = (acc["units"] * pair_bytes / (acc["ms"] / 1e3) / 1e9) if acc["ms"] else None
+    traffic = None  # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/), scaled to this run's mean launch
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            tr = json.load(f)
+        if args.curve == "bls12_381" and acc["launches"]:
+            traffic = tr["dram_bytes_per_pair"] * acc["units"] / acc["launches"]
+    except Exception:
+        pass
     line = {
         "metric": "prover_constraints_per_sec", "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -235,7 +243,8 @@ def main():
                 "d2h_bytes_per_step": len(proof) + 15 * 96},
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                     "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None, "peak_source": peak_kind,
+                     "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_source": peak_kind,
+                     "algorithmic_bytes_per_launch": (acc["units"] * pair_bytes / acc["launches"]) if acc["launches"] else None,
                      "algorithmic_bytes_per_pair": pair_bytes,
                      "note": "integer-ALU bound (profiles/r01_microbench_int_alu.json); see DESIGN.md Rooflines"},
         "kernels": kern, "phases_ms": phases, "dev_ms_steps": dev_ms, "setup_s": setup_s, "proof_bytes": len(proof),
