@@ -10,8 +10,9 @@ timed region exactly as in benches/bench.rs:79-101.
           device->host read of the proof inside the timed region
   roofline     : the dominant kernel (msm_accumulate_kernel) -- algorithmic bytes (128 B per
                  (base, scalar) pair) / CUDA-event kernel time / measured HBM peak
-  cpu_baseline : the oracle's C port of the reference's CPU algorithms timed on this box's host cores
-                 (rank 0, N = 1), on a bounded sample (a smaller instance of the same circuit family)
+  cpu_baseline : the oracle's C++ restatement of the reference prover (oracle/cport/prover.cpp) timed on this
+                 box's host cores (rank 0, N = 1) on a bounded sample: one full prove of a 2^16-constraint
+                 instance of the same circuit family
 
 N > 1 (torchrun, one rank per GPU): every rank runs the prover, each MSM is sharded by base/scalar
 chunk and the partial sums are exchanged with one NCCL all-gather per MSM (DESIGN.md "Multi-GPU");
@@ -109,11 +110,11 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(args):
-    """Oracle C port (oracle/cport) of the reference's CPU algorithms on this box's host cores."""
+def cpu_baseline(args, repeats=1):
+    """Oracle C++ restatement of the reference prover (oracle/cport) on this box's host cores."""
     try:
         from oracle import cport
-        return cport.prover_baseline(args.curve, args.pc, args.cpu_log_n)
+        return cport.prover_baseline(args.curve, args.pc, args.cpu_log_n, repeats=repeats)
     except Exception as e:  # the baseline is reported, never required for the GPU number
         return {"value": None, "unit": "constraints/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
 
@@ -123,13 +124,8 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.time()
-    vals = []
-    base = None
-    for _ in range(max(1, min(args.steps, 3))):
-        base = cpu_baseline(args)
-        if base.get("value"):
-            vals.append(base["value"])
-    v = sum(vals) / len(vals) if vals else None
+    base = cpu_baseline(args, repeats=max(1, min(args.steps, 3)))  # index once, then `steps` (<= 3) full proves
+    v = base.get("value")
     n = 1 << args.cpu_log_n
     line = {
         "impl": "reference", "metric": "prover_constraints_per_sec", "value": v, "unit": "constraints/s", "n_gpus": args.gpus,

@@ -60,9 +60,9 @@ class ZkRng:
 class UniversalSRS:
     """`PC::UniversalParams`, device resident (b2m_srs): G1 powers + the gamma powers the PC needs."""
 
-    def __init__(self, ctx, curve_id, handle, max_degree, powers_limbs):
+    def __init__(self, ctx, curve_id, handle, max_degree, powers_limbs, gamma_limbs=None, gamma_indices=None):
         self.ctx, self.curve_id, self.handle, self.max_degree = ctx, curve_id, handle, max_degree
-        self.powers_limbs = powers_limbs
+        self.powers_limbs, self.gamma_limbs, self.gamma_indices = powers_limbs, gamma_limbs, gamma_indices
 
     def close(self):
         if self.handle:
@@ -156,7 +156,7 @@ class Marlin:
         gamma_limbs = np.ascontiguousarray(gamma_limbs)
         _lib.check(L.b2m_srs_create(self.ctx.handle, self.curve_id, _lib.ptr(powers_limbs), len(powers_limbs), _lib.ptr(gamma_limbs),
                                     _lib.ptr(gi), len(gi), window_bits, ctypes.byref(h)))
-        return UniversalSRS(self.ctx, self.curve_id, h, len(powers_limbs) - 1, powers_limbs)
+        return UniversalSRS(self.ctx, self.curve_id, h, len(powers_limbs) - 1, powers_limbs, gamma_limbs, [int(i) for i in gi])
 
     # -- PC::commit (Level 1) ------------------------------------------------------------------------------
     def commit(self, srs, polys, zk_rng=None):

@@ -1,79 +1,4 @@
-/* oracle/cport -- C restatement (OpenMP) of the reference's CPU algorithms for the prover hot path:
- * ark-ec `VariableBaseMSM::multi_scalar_mul` and ark-poly radix-2 FFT, over ark-ff style Montgomery
- * fields.  TEST INFRASTRUCTURE: used by tests/ as a fast checker at sizes the Python oracle cannot reach
- * and by bench.py as the CPU baseline ("kind": "port").  The reference itself (Rust, un-vendored crates)
- * cannot be built in this environment; parity of this port is pinned against the Python oracle (tests). */
-#include <stdint.h>
-#include <stdlib.h>
-#include <string.h>
-#include <time.h>
-#ifdef _OPENMP
-#include <omp.h>
-#endif
-typedef uint64_t u64;
-typedef unsigned __int128 u128;
-
-#define FP f4
-#define NL 4
-#include "fp_impl.h"
-#undef FP
-#undef NL
-#define FP f6
-#define NL 6
-#include "fp_impl.h"
-#undef FP
-#undef NL
-
-#define FQ f6
-#define G bls
-#include "g1_impl.h"
-#undef FQ
-#undef G
-#define FQ f4
-#define G bn
-#include "g1_impl.h"
-#undef FQ
-#undef G
-
-/* ---- field contexts (moduli: SURVEY.md App. C); R, R^2, -p^-1 derived at init --------------------------- */
-static f4_ctx BLS_FR, BN_FR, BN_FQ;
-static f6_ctx BLS_FQ;
-static int inited = 0;
-static const u64 BLS_FR_P[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull};
-static const u64 BLS_FQ_P[6] = {0xb9feffffffffaaabull, 0x1eabfffeb153ffffull, 0x6730d2a0f6b0f624ull, 0x64774b84f38512bfull, 0x4b1ba7b6434bacd7ull, 0x1a0111ea397fe69aull};
-static const u64 BN_FR_P[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
-static const u64 BN_FQ_P[4] = {0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
-static const u64 BLS_FR_GEN = 7, BN_FR_GEN = 5;
-static const int BLS_FR_S = 32, BN_FR_S = 28;
-
-static u64 neg_inv64(u64 p0) { u64 x = 1; for (int i = 0; i < 6; i++) x *= 2 - p0 * x; return (u64)0 - x; }
-/* r = 2^k mod p by repeated doubling */
-static void pow2_mod(u64* r, const u64* p, int nl, int k) {
-  memset(r, 0, 8 * nl); r[0] = 1;
-  for (int i = 0; i < k; i++) {
-    u64 cy = 0;
-    for (int j = 0; j < nl; j++) { u64 n = (r[j] << 1) | cy; cy = r[j] >> 63; r[j] = n; }
-    int ge = cy != 0;
-    if (!ge) { ge = 1; for (int j = nl - 1; j >= 0; j--) if (r[j] != p[j]) { ge = r[j] > p[j]; break; } }
-    if (ge) { u128 br = 0; for (int j = 0; j < nl; j++) { u128 t = (u128)r[j] - p[j] - (u64)br; r[j] = (u64)t; br = (t >> 64) & 1; } }
-  }
-}
-static void init_all(void) {
-  if (inited) return;
-  memcpy(BLS_FR.p, BLS_FR_P, 32); BLS_FR.inv = neg_inv64(BLS_FR_P[0]); pow2_mod(BLS_FR.r, BLS_FR_P, 4, 256); pow2_mod(BLS_FR.r2, BLS_FR_P, 4, 512);
-  memcpy(BN_FR.p, BN_FR_P, 32); BN_FR.inv = neg_inv64(BN_FR_P[0]); pow2_mod(BN_FR.r, BN_FR_P, 4, 256); pow2_mod(BN_FR.r2, BN_FR_P, 4, 512);
-  memcpy(BN_FQ.p, BN_FQ_P, 32); BN_FQ.inv = neg_inv64(BN_FQ_P[0]); pow2_mod(BN_FQ.r, BN_FQ_P, 4, 256); pow2_mod(BN_FQ.r2, BN_FQ_P, 4, 512);
-  memcpy(BLS_FQ.p, BLS_FQ_P, 48); BLS_FQ.inv = neg_inv64(BLS_FQ_P[0]); pow2_mod(BLS_FQ.r, BLS_FQ_P, 6, 384); pow2_mod(BLS_FQ.r2, BLS_FQ_P, 6, 768);
-  inited = 1;
-}
-static double now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
-static int max_threads(void) {
-#ifdef _OPENMP
-  return omp_get_max_threads();
-#else
-  return 1;
-#endif
-}
+#include "cport_core.h"
 
 /* ---- MSM ------------------------------------------------------------------------------------------------ */
 /* bases: affine x||y Montgomery limbs ((0,0) = infinity); scalars: canonical 4-limb integers; out: affine. */
@@ -105,57 +30,6 @@ int cport_gen_bases(int curve, const u64* g_xy, size_t n, u64* out) {
   return 0;
 }
 
-/* ---- radix-2 FFT over Fr (natural order in and out; inverse scales by 1/n) ------------------------------ */
-static void fr_root(f4_t* w, const f4_ctx* c, u64 gen, int two_adicity, int log_n) {
-  /* TWO_ADIC_ROOT = gen^((p-1)/2^s); w_n = root^(2^(s - log_n)) */
-  u64 e[4]; memcpy(e, c->p, 32); e[0] -= 1;
-  for (int k = 0; k < two_adicity; k++) { for (int j = 0; j < 4; j++) { e[j] = (e[j] >> 1) | (j < 3 ? e[j + 1] << 63 : 0); } }
-  f4_t g = {{gen, 0, 0, 0}}; f4_to_mont(&g, &g, c);
-  f4_pow(w, &g, e, 4, c);
-  for (int k = 0; k < two_adicity - log_n; k++) f4_sqr(w, w, c);
-}
-static void fr_fft(f4_t* a, int log_n, int inverse, const f4_ctx* c, u64 gen, int s, int threads) {
-  size_t n = (size_t)1 << log_n;
-  if (log_n == 0) return;
-  f4_t w; fr_root(&w, c, gen, s, log_n);
-  if (inverse) f4_inv(&w, &w, c);
-  /* twiddle table w^j, j < n/2, built in parallel chunks */
-  f4_t* tw = (f4_t*)malloc(sizeof(f4_t) * (n / 2 ? n / 2 : 1));
-  size_t half = n / 2;
-  #pragma omp parallel num_threads(threads)
-  {
-    int nt = 1, id = 0;
-#ifdef _OPENMP
-    nt = omp_get_num_threads(); id = omp_get_thread_num();
-#endif
-    size_t lo = half * id / nt, hi = half * (id + 1) / nt;
-    if (lo < hi) {
-      u64 e[1] = {lo}; f4_t cur; f4_pow(&cur, &w, e, 1, c);
-      for (size_t j = lo; j < hi; j++) { tw[j] = cur; f4_mul(&cur, &cur, &w, c); }
-    }
-  }
-  /* bit reversal */
-  for (size_t i = 0; i < n; i++) {
-    size_t r = 0; for (int b = 0; b < log_n; b++) r |= ((i >> b) & 1) << (log_n - 1 - b);
-    if (i < r) { f4_t t = a[i]; a[i] = a[r]; a[r] = t; }
-  }
-  for (int st = 1; st <= log_n; st++) {
-    size_t len = (size_t)1 << st, hl = len / 2, step = n / len;
-    #pragma omp parallel for num_threads(threads) schedule(static)
-    for (size_t k = 0; k < n / 2; k++) {
-      size_t blk = k / hl, j = k % hl, i0 = blk * len + j, i1 = i0 + hl;
-      f4_t v; f4_mul(&v, &a[i1], &tw[j * step], c);
-      f4_t u = a[i0];
-      f4_add(&a[i0], &u, &v, c); f4_sub(&a[i1], &u, &v, c);
-    }
-  }
-  if (inverse) {
-    f4_t ninv = {{(u64)n, 0, 0, 0}}; f4_to_mont(&ninv, &ninv, c); f4_inv(&ninv, &ninv, c);
-    #pragma omp parallel for num_threads(threads)
-    for (size_t i = 0; i < n; i++) f4_mul(&a[i], &a[i], &ninv, c);
-  }
-  free(tw);
-}
 int cport_fft(int curve, u64* data, unsigned log_n, int inverse, int threads) {
   init_all();
   if (threads <= 0) threads = max_threads();
@@ -164,61 +38,4 @@ int cport_fft(int curve, u64* data, unsigned log_n, int inverse, int threads) {
   return 0;
 }
 
-/* ---- dominant-kernel schedule of one `Marlin::prove` ----------------------------------
- * Times exactly the MSMs and FFTs the reference issues for a DummyCircuit proof with 2^log_n constraints
- * (|H| = 2^log_n, |K| = 4|H|): MarlinKZG10 15 MSMs / SonicKZG10 11 MSMs and the 21 transforms of
- * src/ahp/prover.rs, on random data.  Pointwise passes, batch inversions, divisions and witness synthesis
- * are NOT included, so the figure is an upper bound on the reference prover's speed on this host. */
-static u64 rng_state = 0x9e3779b97f4a7c15ull;
-static u64 rnd64(void) { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return rng_state; }
-int cport_prover_kernels(int curve, int sonic, unsigned log_n, int threads, int fft_threads, double* out_msm_s, double* out_fft_s, double* out_pairs, double* out_points) {
-  init_all();
-  if (threads <= 0) threads = max_threads();
-  if (fft_threads <= 0) fft_threads = threads;
-  size_t H = (size_t)1 << log_n, K = 4 * H;
-  const f4_ctx* fr = curve == 0 ? &BLS_FR : &BN_FR;
-  /* MSM sizes (in coefficients): w, z_a, z_b, mask | t, g_1 (+shifted), h_1 | g_2 (+shifted), h_2 | open beta (+shifted), open gamma (+shifted) */
-  size_t msm_marlin[15] = {H, H + 1, H + 1, 3 * H, H, H - 1, H - 1, 2 * H, K - 1, K - 1, K - 1, 3 * H - 1, H - 2, K - 1, K - 2};
-  size_t msm_sonic[11] = {H, H + 1, H + 1, 3 * H, H, H - 1, 2 * H, K - 1, K - 1, 3 * H - 1, K - 1};
-  size_t* msizes = sonic ? msm_sonic : msm_marlin;
-  int nm = sonic ? 11 : 15;
-  size_t maxn = K;
-  size_t lq = curve == 0 ? 6 : 4;
-  u64* bases = (u64*)malloc(8 * 2 * lq * maxn);
-  u64 g_bls[12], g_bn[8];
-  /* any curve point will do as the generator of the timing bases: take (x, y) from the standard generators, Montgomery form */
-  {
-    static const u64 GX[6] = {0xfb3af00adb22c6bbull, 0x6c55e83ff97a1aefull, 0xa14e3a3f171bac58ull, 0xc3688c4f9774b905ull, 0x2695638c4fa9ac0full, 0x17f1d3a73197d794ull};
-    static const u64 GY[6] = {0x0caa232946c5e7e1ull, 0xd03cc744a2888ae4ull, 0x00db18cb2c04b3edull, 0xfcf5e095d5d00af6ull, 0xa09e30ed741d8ae4ull, 0x08b3f481e3aaa0f1ull};
-    f6_t x, y; memcpy(x.l, GX, 48); memcpy(y.l, GY, 48); f6_to_mont(&x, &x, &BLS_FQ); f6_to_mont(&y, &y, &BLS_FQ);
-    memcpy(g_bls, x.l, 48); memcpy(g_bls + 6, y.l, 48);
-    f4_t a = {{1, 0, 0, 0}}, b = {{2, 0, 0, 0}}; f4_to_mont(&a, &a, &BN_FQ); f4_to_mont(&b, &b, &BN_FQ);
-    memcpy(g_bn, a.l, 32); memcpy(g_bn + 4, b.l, 32);
-  }
-  cport_gen_bases(curve, curve == 0 ? g_bls : g_bn, maxn, bases);
-  u64* scal = (u64*)malloc(32 * maxn);
-  for (size_t i = 0; i < 4 * maxn; i++) scal[i] = rnd64();
-  for (size_t i = 0; i < maxn; i++) scal[4 * i + 3] &= 0x0fffffffffffffffull; /* < modulus */
-  double tm = 0, pairs = 0;
-  u64 out[12];
-  for (int k = 0; k < nm; k++) {
-    double t0 = now();
-    cport_msm(curve, bases, scal, msizes[k], out, threads);
-    tm += now() - t0; pairs += (double)msizes[k];
-  }
-  /* FFTs: 6 of size |H|, 8 of size 4|H|, 2 of size |K|, 3 of size 2|K| */
-  int flog[4] = {(int)log_n, (int)log_n + 2, (int)log_n + 2, (int)log_n + 3};
-  int fcnt[4] = {6, 8, 2, 3};
-  f4_t* buf = (f4_t*)malloc(sizeof(f4_t) * (2 * K));
-  for (size_t i = 0; i < 2 * K; i++) { buf[i].l[0] = rnd64(); buf[i].l[1] = rnd64(); buf[i].l[2] = rnd64(); buf[i].l[3] = rnd64() & 0x0fffffffffffffffull; }
-  double tf = 0, points = 0;
-  for (int g = 0; g < 4; g++) for (int r = 0; r < fcnt[g]; r++) {
-    double t0 = now();
-    fr_fft(buf, flog[g], r & 1, fr, curve == 0 ? BLS_FR_GEN : BN_FR_GEN, curve == 0 ? BLS_FR_S : BN_FR_S, fft_threads);
-    tf += now() - t0; points += (double)((size_t)1 << flog[g]);
-  }
-  free(buf); free(scal); free(bases);
-  *out_msm_s = tm; *out_fft_s = tf; *out_pairs = pairs; *out_points = points;
-  return 0;
-}
 int cport_max_threads(void) { return max_threads(); }

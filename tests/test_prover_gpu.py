@@ -270,3 +270,36 @@ def test_pc_commit_level1(gctx, scheme):
 def ec_scalar(curve, k):
     from oracle import ec
     return ec.scalar_mul(curve, k, curve.g)
+
+
+@pytest.mark.parametrize("curve_name,scheme,log_n", [("bls12_381", "marlin_kzg10", 14), ("bls12_381", "sonic_kzg10", 14), ("bn254", "marlin_kzg10", 13)])
+def test_bytes_match_cpp_cpu_prover(gctx, curve_name, scheme, log_n):
+    """Byte-exact parity at sizes the Python oracle cannot prove: the same GPU-generated SRS, the same instance and
+    RNG seed go to libb2m (CUDA) and to oracle/cport/prover.cpp (the C++ restatement of the reference prover, itself
+    pinned to the Python specification on the golden fixtures); index_vk bytes, proof bytes and the RNG position
+    must coincide."""
+    from oracle import cport
+    n = 1 << log_n
+    cid = 0 if curve_name == "bls12_381" else 1
+    a, b = 0x1234567890abcdef1234567890abcdef, 0xfedcba0987654321fedcba0987654321
+    m = api.Marlin(curve_name, scheme, ctx=gctx)
+    srs = m.universal_setup(n, n, 3 * n, beta=0x5eed5eed5eed5eed5eed5eed, gamma=7, degree_bounds=(n - 2, 4 * n - 2))
+    circ = gr1cs.dummy_circuit(cid, a, b, 10, n)
+    try:
+        pk = m.index(srs, circ)
+        try:
+            rng = api.ZkRng(bytes(range(32)), 12)
+            gproof = m.prove(pk, circ, rng)
+            cp = cport.CpuProver(curve_name, scheme, srs.powers_limbs, srs.gamma_limbs, srs.gamma_indices, circ.num_constraints,
+                                 circ.num_variables, circ.num_instance, circ.a, circ.b, circ.c)
+            try:
+                assert cp.vk_bytes == pk.vk_bytes
+                cproof, pos, _ = cp.prove(circ.instance, circ.witness, bytes(range(32)), 12, 0)
+                assert cproof == gproof
+                assert pos == rng.word_pos
+            finally:
+                cp.close()
+        finally:
+            pk.close()
+    finally:
+        srs.close()
