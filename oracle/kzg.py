@@ -300,10 +300,12 @@ def open_combinations(engine, ck, lcs, polys, rands, query_set, opening_challeng
     return proofs
 
 
-def check_combinations(ck, lcs, commitments, degree_bounds, query_set, evaluations, proofs, opening_challenge):
-    """`PC::check_combinations` with the pairing replaced by the trapdoor identity (module docstring).
-    commitments: {label: Commitment}; degree_bounds: {label: bound or None};
-    evaluations: {(lc_label, point): value}."""
+def check_combinations(ck, lcs, commitments, degree_bounds, query_set, evaluations, proofs, opening_challenge, g2=None):
+    """`PC::check_combinations`.  g2 = None: the pairing is replaced by the trapdoor identity (module docstring).
+    g2 = G2Key: the reference's own check, a product of pairings [U kzg10::check / sonic_pc check]:
+        e(C - v g - rv gamma_g, h) * prod_d e(C_d, beta^-(D-d) h) * e(-W, beta h - z h) == 1
+    (the middle factors only for SonicKZG10's degree-bounded commitments).
+    commitments: {label: Commitment}; degree_bounds: {label: bound or None}; evaluations: {(lc_label, point): value}."""
     curve = ck.curve
     pp = ck.pp
     p = curve.fr.p
@@ -334,30 +336,58 @@ def check_combinations(ck, lcs, commitments, degree_bounds, query_set, evaluatio
     ok = True
     for (point_label, (w, random_v)) in zip(sorted(by_point), proofs):
         point, labels = by_point[point_label]
-        combined_comm, combined_value = None, 0
+        plain, combined_value = None, 0
+        by_bound = {}  # sonic: bound -> combined commitment made with shifted powers
         counter = 0
         for label in sorted(labels):
             ch = pow(opening_challenge, counter, p)
             counter += 1
             c = lc_comm[label]
             v = evals[(label, point)]
-            base_comm = c.comm
-            if ck.scheme == SONIC and lc_bound[label] is not None:
-                # sonic_pc pairs a bounded commitment with beta^-(D-d) H; through the trapdoor: unshift it
-                unshift = pow(pow(pp.beta, pp.max_degree - lc_bound[label], p), -1, p)
-                base_comm = ec.scalar_mul(curve, unshift, c.comm)
-            combined_comm = ec.affine_add(curve, combined_comm, ec.scalar_mul(curve, ch, base_comm))
             combined_value = (combined_value + v * ch) % p
+            if ck.scheme == SONIC and lc_bound[label] is not None:
+                d = lc_bound[label]
+                by_bound[d] = ec.affine_add(curve, by_bound.get(d), ec.scalar_mul(curve, ch, c.comm))
+                continue
+            plain = ec.affine_add(curve, plain, ec.scalar_mul(curve, ch, c.comm))
             if ck.scheme == MARLIN and lc_bound[label] is not None:
                 ch1 = pow(opening_challenge, counter, p)
                 counter += 1
                 shift_power = pp.powers_of_g[pp.max_degree - lc_bound[label]]
                 adjusted = ec.affine_add(curve, c.shifted, ec.affine_neg(curve, ec.scalar_mul(curve, v, shift_power)))
-                combined_comm = ec.affine_add(curve, combined_comm, ec.scalar_mul(curve, ch1, adjusted))
-        # C - v*g - rv*gamma_g == (beta - z) * W
-        lhs = ec.affine_add(curve, combined_comm, ec.affine_neg(curve, ec.scalar_mul(curve, combined_value, pp.g)))
+                plain = ec.affine_add(curve, plain, ec.scalar_mul(curve, ch1, adjusted))
+        # the combined value is taken out of the unshifted side: C - v g - rv gamma_g
+        plain = ec.affine_add(curve, plain, ec.affine_neg(curve, ec.scalar_mul(curve, combined_value, pp.g)))
         if random_v is not None:
-            lhs = ec.affine_add(curve, lhs, ec.affine_neg(curve, ec.scalar_mul(curve, random_v, pp.gamma_g)))
-        rhs = ec.scalar_mul(curve, (pp.beta - point) % p, w)
-        ok = ok and (lhs == rhs)
+            plain = ec.affine_add(curve, plain, ec.affine_neg(curve, ec.scalar_mul(curve, random_v, pp.gamma_g)))
+        if g2 is None:
+            # trapdoor: unshift the bounded parts (multiply by beta^-(D-d)) and compare with (beta - z) W
+            lhs = plain
+            for d, cd in by_bound.items():
+                unshift = pow(pow(pp.beta, pp.max_degree - d, p), -1, p)
+                lhs = ec.affine_add(curve, lhs, ec.scalar_mul(curve, unshift, cd))
+            ok = ok and (lhs == ec.scalar_mul(curve, (pp.beta - point) % p, w))
+        else:
+            ok = ok and g2.check(curve, plain, by_bound, w, point)
     return ok
+
+
+class G2Key:
+    """The G2 half of the verifier key: h, beta h and (SonicKZG10) beta^-(D-d) h per enforced bound, produced
+    at setup.  `check` runs the pairing product of the reference's KZG10 / Sonic checks (oracle/pairing.py)."""
+
+    def __init__(self, pp, bounds=()):
+        from . import pairing
+        self.pairing = pairing
+        self.h = pairing.g2_generator()
+        self.beta_h = pairing.e12_mul(pp.beta, self.h)
+        p = pp.curve.fr.p
+        self.neg_powers = {d: pairing.e12_mul(pow(pow(pp.beta, pp.max_degree - d, p), -1, p), self.h) for d in bounds}
+
+    def check(self, curve, plain, by_bound, w, z):
+        pg = self.pairing
+        rhs_g2 = pg.e12_add(self.beta_h, pg.e12_neg(pg.e12_mul(z % curve.fr.p, self.h)))  # beta h - z h
+        pairs = [(plain, self.h), (ec.affine_neg(curve, w), rhs_g2)]
+        for d, cd in by_bound.items():
+            pairs.append((cd, self.neg_powers[d]))
+        return pg.pairing_product_is_one(pairs)

@@ -129,8 +129,9 @@ def prove(pk, circuit, zk_rng, engine=None):
     return proof
 
 
-def verify(pk, public_input, proof):
-    """[R src/lib.rs:315-433] with `PC::check_combinations` done through the trapdoor (kzg.py)."""
+def verify(pk, public_input, proof, g2=None):
+    """[R src/lib.rs:315-433].  g2 = None: `PC::check_combinations` through the SRS trapdoor (kzg.py);
+    g2 = kzg.G2Key: through the pairing product the reference computes (BLS12-381 only)."""
     curve, scheme, ck = pk.curve, pk.scheme, pk.ck
     f = curve.fr
     p = f.p
@@ -169,7 +170,7 @@ def verify(pk, public_input, proof):
     for q, e in zip(eval_labels, proof.evaluations):
         evaluations[q] = e
     lcs = ahp.construct_linear_combinations(f, public_input, lambda l, pt: evaluations[(l, pt)], vs)
-    return kzg.check_combinations(ck, lcs, commitments, degree_bounds, query_set, evaluations, proof.pc_proof, opening_challenge)
+    return kzg.check_combinations(ck, lcs, commitments, degree_bounds, query_set, evaluations, proof.pc_proof, opening_challenge, g2)
 
 
 # ---- CanonicalSerialize -----------------------------------------------------------------------

@@ -224,3 +224,33 @@ def test_cpp_prover_reproduces_golden(case):
         assert proof.hex() == g["proof_hex"] and pos == g["zk_rng_word_pos_after"]
     finally:
         cp.close()
+
+
+def test_pairing_bilinear_and_nondegenerate():
+    from oracle import pairing as pg
+    c = BLS12_381
+    Q = pg.g2_generator()
+    e1 = pg.pairing(c.g, Q)
+    assert e1 != pg.Fq12.one() and e1.pow(pg.R) == pg.Fq12.one()
+    a, b = 0x1234567, 0x7654321
+    assert pg.pairing(ec.scalar_mul(c, a, c.g), pg.e12_mul(b, Q)) == e1.pow(a * b % pg.R)
+    assert pg.pairing_product_is_one([(ec.scalar_mul(c, a, c.g), Q), (ec.affine_neg(c, c.g), pg.e12_mul(a, Q))])
+
+
+@pytest.mark.parametrize("scheme", [kzg.MARLIN, kzg.SONIC])
+def test_verify_with_real_pairings(scheme):
+    """The reference's own acceptance test [src/test.rs:158-161] with `KZG10::check` done by pairings, no trapdoor."""
+    curve = BLS12_381
+    f = curve.fr
+    rng = R.test_rng()
+    a, b = R.field_rand(f, rng), R.field_rand(f, rng)
+    c = a * b % f.p
+    d = c * b % f.p
+    circ = r1cs.test_circuit(f, a, b, 25, 25)
+    srs = marlin.universal_setup(curve, 32, 32, 100, beta=0xfeedbeef1234, g_scalar=7, gamma=13)
+    eng = kzg.Engine(use_trapdoor=True)
+    pk = marlin.index(srs, circ, scheme, eng)
+    proof = marlin.prove(pk, circ, rng, eng)
+    g2 = kzg.G2Key(srs, pk.ck.enforced_degree_bounds)
+    assert marlin.verify(pk, [c, d], proof, g2)
+    assert not marlin.verify(pk, [a, a], proof, g2)
