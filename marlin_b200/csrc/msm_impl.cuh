@@ -528,10 +528,8 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       B2M_CHECK_LAUNCH();
       cx.launches++;
       cx.span_end(sp);
-      size_t nparts = 2 * (size_t)div_up(nthreads, 128) * 128;
       size_t sp1 = cx.span_begin("msm_stitch", (double)n);
       n_long.zero();
-      (void)nparts;
       msm_stitch_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, nthreads, q, offsets.p, cursor.p,
                                                                            buckets.p + (size_t)j * B, long_runs.p, n_long.p, long_cap);
       msm_stitch_long_kernel<Fq><<<2 * cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, long_runs.p, n_long.p, long_cap,
