@@ -136,6 +136,19 @@ int b2m_pc_commit(b2m_srs* srs, int pc_variant, size_t n_polys, const uint64_t* 
                   b2m_rng* rng, uint64_t* out_comm_xy, uint64_t* out_shifted_xy, uint64_t* out_rand,
                   uint64_t* out_shifted_rand, size_t rand_stride);
 
+/* Replaces `PC::open_individual_opening_challenges(ck, polynomials, commitments, point, challenges, rands)`
+ * for one point [U ark-poly-commit 0.3 marlin_pc/mod.rs, sonic_pc/mod.rs -> kzg10::KZG10::open], the call the
+ * generic `open_combinations` / `batch_open` code ends in (reference src/lib.rs:292-302).  Polynomials and their
+ * commitment randomness are given in query order; challenge k is opening_challenge^k starting at k = 0
+ * (MarlinKZG10 spends a second challenge on every degree-bounded polynomial).  max_degree_bound: the largest
+ * enforced bound of the committer key (MarlinKZG10 shifted powers), -1 if none.
+ * Output: the `kzg10::Proof { w, random_v }`. */
+int b2m_pc_open(b2m_srs* srs, int pc_variant, size_t n_polys, const uint64_t* const* coeffs,
+                const size_t* n_coeffs, const int64_t* degree_bounds, const uint64_t* rands,
+                const uint64_t* shifted_rands, size_t rand_stride, int64_t max_degree_bound,
+                const uint64_t* point, const uint64_t* opening_challenge, uint64_t* out_w_xy,
+                int* out_has_random_v, uint64_t* out_random_v);
+
 /* ---- Level 2: prover ABI ---------------------------------------------------------------- */
 
 /* R1CS matrix in CSR form, as `ConstraintSystem::to_matrices()` yields it

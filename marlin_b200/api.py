@@ -180,6 +180,27 @@ class Marlin:
                                    _lib.ptr(srand), 4))
         return comm, shifted, rand, srand
 
+    def open(self, srs, polys, rands, shifted_rands, point_limbs, challenge_limbs, max_degree_bound=None):
+        """`PC::open_individual_opening_challenges` at one point [U marlin_pc / sonic_pc open].  polys as in `commit`
+        (coeff limbs, degree_bound, _), rands / shifted_rands as returned by `commit`; point and opening challenge are
+        Montgomery Fr limbs.  Returns (w affine limbs, random_v limbs or None)."""
+        L = _lib.lib()
+        n = len(polys)
+        lq = _lib.LIMBS[self.curve_id][1]
+        arrs = [np.ascontiguousarray(p[0], dtype=np.uint64) for p in polys]
+        ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        lens = (ctypes.c_size_t * n)(*[len(a) for a in arrs])
+        db = (ctypes.c_int64 * n)(*[-1 if p[1] is None else p[1] for p in polys])
+        rands = np.ascontiguousarray(rands, dtype=np.uint64)
+        shifted_rands = np.ascontiguousarray(shifted_rands, dtype=np.uint64)
+        w = np.zeros(2 * lq, dtype=np.uint64)
+        rv = np.zeros(4, dtype=np.uint64)
+        has = ctypes.c_int(0)
+        _lib.check(L.b2m_pc_open(srs.handle, self.pc, n, ptrs, lens, db, _lib.ptr(rands), _lib.ptr(shifted_rands), rands.shape[1],
+                                 -1 if max_degree_bound is None else max_degree_bound, _lib.ptr(np.ascontiguousarray(point_limbs)),
+                                 _lib.ptr(np.ascontiguousarray(challenge_limbs)), _lib.ptr(w), ctypes.byref(has), _lib.ptr(rv)))
+        return w, (rv if has.value else None)
+
     # -- index -----------------------------------------------------------------------------------------
     def index(self, srs, r1cs):
         """[reference src/lib.rs:100-148] -> IndexProverKey (device resident); .vk_bytes is `index_vk` (ToBytes)."""

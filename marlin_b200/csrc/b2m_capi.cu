@@ -159,6 +159,25 @@ int b2m_pc_commit(b2m_srs* srs, int pc_variant, size_t n_polys, const uint64_t* 
   });
 }
 
+int b2m_pc_open(b2m_srs* srs, int pc_variant, size_t n_polys, const uint64_t* const* coeffs, const size_t* n_coeffs,
+                const int64_t* degree_bounds, const uint64_t* rands, const uint64_t* shifted_rands, size_t rand_stride,
+                int64_t max_degree_bound, const uint64_t* point, const uint64_t* opening_challenge, uint64_t* out_w_xy,
+                int* out_has_random_v, uint64_t* out_random_v) {
+  return guard([&] {
+    B2M_REQUIRE(srs && coeffs && n_coeffs && degree_bounds && point && opening_challenge && out_w_xy && out_has_random_v && out_random_v,
+                B2M_ERR_INVALID_ARG, "null argument");
+    B2M_REQUIRE(pc_variant == B2M_PC_MARLIN_KZG10 || pc_variant == B2M_PC_SONIC_KZG10, B2M_ERR_INVALID_ARG, "unknown PC variant");
+    B2M_REQUIRE(n_polys >= 1, B2M_ERR_INVALID_ARG, "no polynomials");
+    srs->ctx->cx.use();
+    if (srs->curve == B2M_CURVE_BLS12_381)
+      pc_open_bls(srs, pc_variant, n_polys, coeffs, n_coeffs, degree_bounds, rands, shifted_rands, rand_stride, max_degree_bound, point,
+                  opening_challenge, out_w_xy, out_has_random_v, out_random_v);
+    else
+      pc_open_bn(srs, pc_variant, n_polys, coeffs, n_coeffs, degree_bounds, rands, shifted_rands, rand_stride, max_degree_bound, point,
+                 opening_challenge, out_w_xy, out_has_random_v, out_random_v);
+  });
+}
+
 // ---- Level 2 ----------------------------------------------------------------------------------
 struct b2m_index {
   b2m_srs* srs;

@@ -12,4 +12,10 @@ void pc_commit_bn(b2m_srs* srs, int pc, size_t n_polys, const uint64_t* const* c
   pc_commit_impl<FrBn, FqBn>(srs, *srs->bn, pc, n_polys, coeffs, n_coeffs, degree_bounds, hiding_bounds, rng, out_comm_xy, out_shifted_xy, out_rand,
                              out_shifted_rand, rand_stride);
 }
+void pc_open_bn(b2m_srs* srs, int pc, size_t n_polys, const uint64_t* const* coeffs, const size_t* n_coeffs, const int64_t* degree_bounds,
+                 const uint64_t* rands, const uint64_t* shifted_rands, size_t rand_stride, int64_t max_degree_bound, const uint64_t* point,
+                 const uint64_t* opening_challenge, uint64_t* out_w_xy, int* out_has_random_v, uint64_t* out_random_v) {
+  pc_open_impl<FrBn, FqBn>(srs, srs->ctx->ntt_bn(), *srs->bn, pc, n_polys, coeffs, n_coeffs, degree_bounds, rands, shifted_rands, rand_stride,
+                           max_degree_bound, point, opening_challenge, out_w_xy, out_has_random_v, out_random_v);
+}
 }  // namespace b2m

@@ -977,4 +977,110 @@ void pc_commit_impl(b2m_srs* srs, Msm<Fr, Fq>& msm, int pc, size_t n_polys, cons
   if (rng) rng->word_pos = zk.word_pos;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Level 1: `PC::open_individual_opening_challenges` at one point [U ark-poly-commit marlin_pc / sonic_pc open]
+// ---------------------------------------------------------------------------------------------------
+template <class Fr, class Fq>
+void pc_open_impl(b2m_srs* srs, Ntt<Fr>& ntt, Msm<Fr, Fq>& msm, int pc, size_t n_polys, const uint64_t* const* coeffs,
+                  const size_t* n_coeffs, const int64_t* degree_bounds, const uint64_t* rands, const uint64_t* shifted_rands,
+                  size_t rand_stride, int64_t max_degree_bound, const uint64_t* point, const uint64_t* opening_challenge,
+                  uint64_t* out_w_xy, int* out_has_random_v, uint64_t* out_random_v) {
+  using Pt = Affine<Fq>;
+  using Xy = XYZZ<Fq>;
+  using M = MarlinIndex<Fr, Fq>;
+  typedef typename M::HPoly HPoly;
+  (void)ntt;
+  Ctx& cx = srs->ctx->cx;
+  const size_t D = srs->n_g - 1;
+  const bool marlin = pc == B2M_PC_MARLIN_KZG10;
+  Fr z, xi;
+  memcpy(z.l, point, sizeof(z.l));
+  memcpy(xi.l, opening_challenge, sizeof(xi.l));
+  const Fr one = Fr::one();
+  auto host_poly = [&](const uint64_t* base, size_t i) {
+    HPoly h;
+    if (!base) return h;
+    for (size_t k = 0; k < rand_stride; k++) {
+      Fr c;
+      memcpy(c.l, base + 4 * (rand_stride * i + k), sizeof(c.l));
+      h.push_back(c);
+    }
+    while (!h.empty() && h.back().is_zero()) h.pop_back();
+    return h;
+  };
+  size_t max_len = 1;
+  for (size_t i = 0; i < n_polys; i++) max_len = std::max(max_len, n_coeffs[i]);
+  std::vector<DBuf<Fr>> dev, keep;
+  DBuf<Fr> comb(cx, max_len), tmp(cx, max_len);
+  comb.zero();
+  std::vector<MsmJob<Fr, Fq>> shifted_jobs;
+  DBuf<Xy> ex(cx, n_polys + 1);
+  int n_extra = 0;
+  HPoly r, sr, srw;
+  Fr ch = one;
+  bool enforce = false;
+  for (size_t i = 0; i < n_polys; i++) {
+    const size_t len = n_coeffs[i];
+    B2M_REQUIRE(len <= srs->n_g, B2M_ERR_DEGREE_TOO_LARGE, "polynomial %zu has %zu coefficients, the SRS %zu powers", i, len, srs->n_g);
+    dev.emplace_back(cx, len ? len : 1);
+    if (len) dev.back().upload(reinterpret_cast<const Fr*>(coeffs[i]), len);
+    // comb += ch * p_i
+    LcTerms<Fr> lt;
+    lt.add(comb.p, max_len, one);
+    lt.add(dev.back().p, len, ch);
+    lincomb_kernel<Fr><<<div_up(max_len, 256), 256, 0, cx.stream>>>(lt, max_len, tmp.p);
+    B2M_CHECK_LAUNCH();
+    cx.launches++;
+    std::swap(comb, tmp);
+    M::hp_axpy(r, ch, host_poly(rands, i));
+    ch = ch * xi;
+    if (marlin && degree_bounds[i] >= 0) {
+      B2M_REQUIRE(max_degree_bound >= degree_bounds[i] && (size_t)max_degree_bound <= D, B2M_ERR_DEGREE_TOO_LARGE, "bad degree bounds");
+      enforce = true;
+      HPoly srand_i = host_poly(shifted_rands, i);
+      if (len > 1) {
+        // shifted witness ch1 * (p_i / (X - z)) against shifted_powers: powers_of_g[D - bound ..]
+        keep.emplace_back(cx, len);
+        DBuf<Fr>& s = keep.back();
+        rec_suffix<Fr>(cx, dev.back().p, s.p, len, 1, z, true);
+        Fr* ps = s.p;
+        const Fr c1 = ch;
+        ew(cx, len - 1, [=] __device__(size_t k) { st_fr(ps + 1 + k, ld_fr(ps + 1 + k) * c1); });
+        shifted_jobs.push_back(MsmJob<Fr, Fq>{s.p + 1, true, len - 1, D - (size_t)degree_bounds[i], nullptr, 0, 0, nullptr, 0, ex.p + n_extra, nullptr});
+        n_extra++;
+      }
+      M::hp_axpy(sr, ch, srand_i);
+      if (!M::hp_is_zero(srand_i)) M::hp_axpy(srw, ch, M::hp_div_linear(srand_i, z));
+      ch = ch * xi;
+    }
+  }
+  // witness of the combination and its hiding part
+  DBuf<Fr> sfx(cx, max_len);
+  rec_suffix<Fr>(cx, comb.p, sfx.p, max_len, 1, z, true);
+  const bool hiding = !M::hp_is_zero(r);
+  HPoly hw = hiding ? M::hp_div_linear(r, z) : HPoly();
+  if (marlin && enforce) M::hp_axpy(hw, one, srw);
+  const Fr* hw_dev = nullptr;
+  if (!hw.empty()) {
+    keep.emplace_back(cx, hw.size());
+    keep.back().upload(hw.data(), hw.size());
+    hw_dev = keep.back().p;
+  }
+  for (size_t at = 0; at < shifted_jobs.size(); at += MSM_MAX_BATCH)
+    msm.run_batch(shifted_jobs.data() + at, (int)std::min<size_t>(MSM_MAX_BATCH, shifted_jobs.size() - at));
+  DBuf<Pt> w(cx, 1);
+  MsmJob<Fr, Fq> fin{sfx.p + 1, true, max_len - 1, 0, hw_dev, hw.size(), hw.empty() ? 0 : srs->gamma_slot(0), ex.p, n_extra, nullptr, w.p};
+  msm.run_batch(&fin, 1);
+  Pt hwp;
+  w.download(&hwp, 1);
+  memcpy(out_w_xy, &hwp, sizeof(hwp));
+  *out_has_random_v = hiding ? 1 : 0;
+  Fr rv = Fr::zero();
+  if (hiding) {
+    rv = M::hp_eval(r, z);
+    if (marlin && enforce) rv = rv + M::hp_eval(sr, z);
+  }
+  memcpy(out_random_v, rv.l, sizeof(rv.l));
+}
+
 }  // namespace b2m

@@ -308,3 +308,46 @@ def test_bytes_match_cpp_cpu_prover(gctx, curve_name, scheme, log_n):
             pk.close()
     finally:
         srs.close()
+
+
+@pytest.mark.parametrize("scheme", list(SCHEMES))
+def test_pc_open_level1(gctx, scheme):
+    """Level-1 ABI (b2m_pc_open) against the oracle's `open_individual_opening_challenges` at one point: same
+    witness commitment w and same random_v, with bounded / unbounded / hiding / non-hiding polynomials mixed."""
+    import random
+    curve = BLS12_381
+    f = curve.fr
+    rnd = random.Random(23)
+    D = 63
+    osrs = kzg.UniversalParams(curve, D, 0xabcdef, ec_scalar(curve, 3), 11)
+    bounds = [10, 40]
+    ck = kzg.CommitterKey(osrs, D, 1, bounds, SCHEMES[scheme])
+    cases = [
+        [kzg.LabeledPoly("a", [rnd.randrange(f.p) for _ in range(20)], None, 1), kzg.LabeledPoly("b", [rnd.randrange(f.p) for _ in range(11)], 10, 1),
+         kzg.LabeledPoly("c", [rnd.randrange(f.p) for _ in range(33)], 40, None), kzg.LabeledPoly("d", [rnd.randrange(f.p) for _ in range(64)], None, None)],
+        [kzg.LabeledPoly("g", [rnd.randrange(f.p) for _ in range(41)], 40, None), kzg.LabeledPoly("h", [rnd.randrange(f.p) for _ in range(50)], None, None)],
+        [kzg.LabeledPoly("k", [rnd.randrange(f.p) for _ in range(9)], None, None)],
+    ]
+    m = api.Marlin("bls12_381", scheme, ctx=gctx)
+    gidx = sorted({0, 1, 2} | ({D - d + i for d in bounds for i in range(3)} if scheme == "sonic_kzg10" else set()))
+    srs = m.srs_from_points(util.points_to_limbs(curve, osrs.powers_of_g), util.points_to_limbs(curve, [osrs.power_of_gamma_g(i) for i in gidx]), gidx)
+    try:
+        for polys in cases:
+            zk = orng.ChaChaRng(bytes(range(32)), 12)
+            eng = kzg.Engine(False)
+            _, orands = kzg.commit(eng, ck, polys, zk)
+            z, xi = rnd.randrange(f.p), rnd.randrange(1 << 128)
+            ow, orv = kzg.open_at_point(eng, ck, polys, orands, z, lambda k: pow(xi, k, f.p))
+            rands = np.zeros((len(polys), 4, 4), dtype=np.uint64)
+            srands = np.zeros((len(polys), 4, 4), dtype=np.uint64)
+            for i, r in enumerate(orands):
+                if r.rand:
+                    rands[i, :len(r.rand)] = util.fr_to_mont_limbs(curve, r.rand)
+                if r.shifted_rand:
+                    srands[i, :len(r.shifted_rand)] = util.fr_to_mont_limbs(curve, r.shifted_rand)
+            gw, grv = m.open(srs, [(util.fr_to_mont_limbs(curve, p.coeffs), p.degree_bound, p.hiding_bound) for p in polys], rands, srands,
+                             util.fr_to_mont_limbs(curve, [z])[0], util.fr_to_mont_limbs(curve, [xi])[0], max_degree_bound=max(bounds))
+            assert util.points_from_limbs(curve, gw)[0] == ow
+            assert (None if grv is None else util.fr_from_mont_limbs(curve, grv)[0]) == orv
+    finally:
+        srs.close()
