@@ -48,12 +48,37 @@ ntt_pass_kernel(const Fr* src, Fr* dst, const Fr* __restrict__ tw, int log_n, in
     return (hi << (k + lb)) + ((size_t)r << lb) + lo;
   };
 
-  for (int idx = tid; idx < R * C; idx += NTT_THREADS) {
-    int r, cc;
-    if (LAST) { r = idx & (R - 1); cc = idx >> k; } else { cc = idx & (C - 1); r = idx >> cols_log; }
-    sm[sidx(r, cc)] = ld_fr(src + gidx(r, cc));
+  // Tile load through the TMA engine (cp.async.bulk, 1-D): every contiguous run of the tile -- one 2^cols_log-element
+  // row (256 B) in the strided passes, one 2^k-element column group in the last pass -- is one bulk copy that
+  // completes on a single mbarrier; no thread spends registers or LSU slots on the staging.
+  __shared__ __align__(8) unsigned long long tile_bar;
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&tile_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  {
+    const int runs = LAST ? C : R;                      // number of contiguous runs in the tile
+    const uint32_t run_bytes = (uint32_t)sizeof(Fr) << (LAST ? k : cols_log);
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(run_bytes * (uint32_t)runs) : "memory");
+    for (int run = tid; run < runs; run += NTT_THREADS) {
+      const Fr* g = LAST ? src + gidx(0, run) : src + gidx(run, 0);
+      const uint32_t dst_addr = (uint32_t)__cvta_generic_to_shared(sm + (LAST ? sidx(0, run) : sidx(run, 0)));
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_addr), "l"(g),
+                   "r"(run_bytes), "r"(bar_addr)
+                   : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+          : "=r"(done)
+          : "r"(bar_addr)
+          : "memory");
+    }
+  }
 
   for (int t = 0; t < k; t++) {
     const int stride_log = k - 1 - t;  // row distance of a butterfly pair = 2^stride_log
