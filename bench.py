@@ -221,6 +221,13 @@ def main():
     acc = kern.get("msm_accumulate_kernel", {"ms": 0.0, "units": 0.0, "launches": 0})
     pair_bytes = 128 if args.curve == "bls12_381" else 96
     achieved = (acc["units"] * pair_bytes / (acc["ms"] / 1e3) / 1e9) if acc["ms"] else None
+    msm_windows, alu_peak = 13, None  # c = 20 => 13 signed windows per scalar (fewer bits per rank when sharded: see DESIGN.md)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_microbench_int_alu.json")) as f:
+            mb = json.load(f)
+        alu_peak = max(v for k, v in mb.items() if k.startswith("g1_madd")) if args.curve == "bls12_381" else None
+    except Exception:
+        pass
     traffic = None  # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/), scaled to this run's mean launch
     try:
         with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
@@ -248,6 +255,13 @@ def main():
                      "algorithmic_bytes_per_launch": (acc["units"] * pair_bytes / acc["launches"]) if acc["launches"] else None,
                      "algorithmic_bytes_per_pair": pair_bytes,
                      "note": "integer-ALU bound (profiles/r01_microbench_int_alu.json); see DESIGN.md Rooflines"},
+        # the meaningful roofline of this kernel: XYZZ mixed additions per second against the whole-chip
+        # integer-multiply microbenchmark (profiles/r01_microbench_int_alu.json, tools/microbench.cu)
+        "roofline_int_alu": {"kernel": "msm_accumulate_kernel", "unit": "G mixed additions/s",
+                             "achieved": (acc["units"] * msm_windows / (acc["ms"] / 1e3) / 1e9) if acc["ms"] else None,
+                             "peak": alu_peak, "frac": (acc["units"] * msm_windows / (acc["ms"] / 1e3) / 1e9 / alu_peak) if acc["ms"] and alu_peak else None,
+                             "peak_source": "tools/microbench.cu g1_madd (measured on this pool's B200)"},
+        "msm_accumulate_ms_per_step": acc["ms"] / args.steps if acc["ms"] else None,
         "kernels": kern, "phases_ms": phases, "dev_ms_steps": dev_ms, "setup_s": setup_s, "proof_bytes": len(proof),
     }
     if rank == 0:

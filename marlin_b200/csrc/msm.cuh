@@ -23,8 +23,9 @@
 
 namespace b2m {
 
-constexpr int MSM_MIN_WINDOW = 8;  // 5 window-id bits in a reference: ceil(256 / c) <= 32
-constexpr int MSM_IDX_BITS = 26;  // point index bits in a sorted reference
+constexpr int MSM_MIN_WINDOW = 8;  // at most ceil(256 / 8) = 32 windows
+constexpr int MSM_BKT_BITS = 24;  // a sorted reference is {table index | sign << 31, bucket | window << 24}
+constexpr uint32_t MSM_BKT_MASK = (1u << MSM_BKT_BITS) - 1;
 constexpr uint32_t MSM_NO_DIGIT = 0xffffffffu;
 constexpr int MSM_MAX_BATCH = 8;   // MSMs per run_batch call
 

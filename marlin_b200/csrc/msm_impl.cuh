@@ -101,7 +101,7 @@ __global__ void msm_digits_kernel(const Fr* scalars, const Fr* scalars2, bool MO
 // ---- 2. exclusive scan of u32: scan.cuh -------------------------------------------------------
 
 // ---- 3. scatter -------------------------------------------------------------------------------
-// Counting sort by bucket: sorted[pos] = {(absolute table index) | w << 26 | sign << 31, bucket}.
+// Counting sort by bucket: sorted[pos] = {(absolute table index) | sign << 31, bucket | window << 24}.
 static __global__ void msm_scatter_kernel(const uint32_t* digits, size_t n, size_t nt, size_t base_off, size_t idx2, int W,
                                           uint32_t* cursor, uint2* sorted) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -112,7 +112,7 @@ static __global__ void msm_scatter_kernel(const uint32_t* digits, size_t n, size
     if (d == MSM_NO_DIGIT) continue;
     uint32_t bkt = d & 0x7fffffffu;
     uint32_t pos = atomicAdd(cursor + bkt, 1u);
-    sorted[pos] = make_uint2(abs_idx | ((uint32_t)w << MSM_IDX_BITS) | (d & 0x80000000u), bkt);  // one 8-byte scattered store
+    sorted[pos] = make_uint2(abs_idx | (d & 0x80000000u), bkt | ((uint32_t)w << MSM_BKT_BITS));  // one 8-byte scattered store
   }
 }
 
@@ -141,9 +141,9 @@ msm_accumulate_kernel(const Affine<Fq>* __restrict__ tables, size_t table_stride
     const uint32_t end = (total - start > q) ? start + q : total;
     uint2 rb = __ldg(sorted + start);
     uint32_t ref = rb.x;
-    uint32_t cur_b = rb.y;
+    uint32_t cur_b = rb.y & MSM_BKT_MASK;
     uint32_t seg_start = start;
-    Affine<Fq> p = ld_affine(tables + (size_t)((ref >> MSM_IDX_BITS) & 31u) * table_stride + (ref & ((1u << MSM_IDX_BITS) - 1)));
+    Affine<Fq> p = ld_affine(tables + (size_t)(rb.y >> MSM_BKT_BITS) * table_stride + (ref & 0x7fffffffu));
     XYZZ<Fq> acc = XYZZ<Fq>::inf();
     for (uint32_t e = start; e < end; e++) {
       Affine<Fq> cur = p;
@@ -152,8 +152,8 @@ msm_accumulate_kernel(const Affine<Fq>* __restrict__ tables, size_t table_stride
       if (e + 1 < end) {
         rb = __ldg(sorted + e + 1);
         ref = rb.x;
-        next_b = rb.y;
-        p = ld_affine(tables + (size_t)((ref >> MSM_IDX_BITS) & 31u) * table_stride + (ref & ((1u << MSM_IDX_BITS) - 1)));
+        next_b = rb.y & MSM_BKT_MASK;
+        p = ld_affine(tables + (size_t)(rb.y >> MSM_BKT_BITS) * table_stride + (ref & 0x7fffffffu));
       }
       acc.add_mixed(cur, neg);
       if (e + 1 == end || next_b != cur_b) {
@@ -393,9 +393,11 @@ __global__ void g1_powers_kernel(Affine<Fq> g, Fr beta, size_t n, Affine<Fq>* ou
 // ---- host driver ------------------------------------------------------------------------------
 template <class Fr, class Fq>
 int Msm<Fr, Fq>::pick_window(size_t n) {
+  // n = (base, scalar) pairs a typical MSM of this key gives ONE GPU.  Cost model: n * ceil(256 / c) mixed additions
+  // in the bucket pass + ~2.8 * 2^(c-1) for the reduction => c ~ log2(n) - 1, at most 20 (13 windows, 2^19 buckets).
   int lg = 0;
   while (((size_t)1 << (lg + 1)) <= n) lg++;
-  int c = lg - 2;
+  int c = lg - 1;
   if (c < MSM_MIN_WINDOW) c = MSM_MIN_WINDOW;
   if (c > 20) c = 20;
   return c;
@@ -404,8 +406,8 @@ int Msm<Fr, Fq>::pick_window(size_t n) {
 template <class Fr, class Fq>
 Msm<Fr, Fq>::Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, const Affine<Fq>* host_extra, size_t n_extra_bases, int window_bits)
     : ctx(&cx), n_srs(n), n_extra(n_extra_bases), stride(n + n_extra_bases) {
-  B2M_REQUIRE(n >= 1 && stride <= ((size_t)1 << MSM_IDX_BITS), B2M_ERR_INVALID_ARG, "SRS size %zu out of range", n);
-  c = window_bits > 0 ? window_bits : pick_window(n);
+  B2M_REQUIRE(n >= 1 && stride < ((size_t)1 << 31), B2M_ERR_INVALID_ARG, "SRS size %zu out of range", n);
+  c = window_bits > 0 ? window_bits : pick_window(n / (size_t)(cx.world > 0 ? cx.world : 1));  // sharded MSMs see n / world pairs per rank
   B2M_REQUIRE(c >= MSM_MIN_WINDOW && c <= 24, B2M_ERR_INVALID_ARG, "window bits %d out of range [%d, 24]", c, MSM_MIN_WINDOW);
   W = (Fr::Params::BITS + 1 + c - 1) / c;
   B2M_REQUIRE(W <= 32, B2M_ERR_INVALID_ARG, "too many windows (%d)", W);
