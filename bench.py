@@ -221,7 +221,10 @@ def main():
     acc = kern.get("msm_accumulate_kernel", {"ms": 0.0, "units": 0.0, "launches": 0})
     pair_bytes = 128 if args.curve == "bls12_381" else 96
     achieved = (acc["units"] * pair_bytes / (acc["ms"] / 1e3) / 1e9) if acc["ms"] else None
-    msm_windows, alu_peak = 13, None  # c = 20 => 13 signed windows per scalar (fewer bits per rank when sharded: see DESIGN.md)
+    from marlin_b200 import _lib as _plib
+    win_bits = int(_plib.lib().b2m_srs_window_bits(srs.handle))
+    scalar_bits = 255 if args.curve == "bls12_381" else 254
+    msm_windows, alu_peak = (scalar_bits + win_bits) // win_bits, None  # signed c-bit windows per scalar (c = 20 -> 13)
     try:
         with open(os.path.join(ROOT, "profiles", "r01_microbench_int_alu.json")) as f:
             mb = json.load(f)
@@ -244,7 +247,7 @@ def main():
                                f"{args.curve}, {args.pc}, SimpleHashFiatShamirRng<Blake2s,ChaChaRng>",
                    "timing": "CUDA events on the library stream around each prove; working set (SRS tables + index + polynomials, "
                              "> 7 GB) exceeds L2, no flush needed",
-                   "msm_window_bits": None, "parallelism": f"msm-shard x{world}" if world > 1 else "single"},
+                   "msm_window_bits": win_bits, "parallelism": f"msm-shard x{world}" if world > 1 else "single"},
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "gpu_launches": launches // args.steps,
         "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": int(circ.instance.nbytes + circ.witness.nbytes),

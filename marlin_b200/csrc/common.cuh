@@ -45,7 +45,8 @@ inline std::string fmt(const char* f, ...) {
 struct Ctx {
   int device = 0;
   int sm_count = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;  // the stream every helper launches on (see StreamSwap)
+  cudaStream_t side = nullptr;    // second stream: sort of the next MSM while the current one accumulates
   cudaMemPool_t pool = nullptr;
   // multi-GPU MSM sharding (comm.cuh): rank / world of this process and its ncclComm_t
   int rank = 0, world = 1;
@@ -104,11 +105,13 @@ struct Ctx {
                 dev, prop.major, prop.minor);
     sm_count = prop.multiProcessorCount;
     B2M_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    B2M_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
     B2M_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
     unsigned long long thr = ~0ull;  // keep freed blocks cached in the pool
     B2M_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
   }
   ~Ctx() {
+    if (side) cudaStreamDestroy(side);
     if (stream) cudaStreamDestroy(stream);
   }
   void use() const { cudaSetDevice(device); }
@@ -122,6 +125,14 @@ struct Ctx {
   void free_bytes(void* p) {
     if (p) cudaFreeAsync(p, stream);
   }
+};
+
+// Issue a scope's work on another stream: every helper (DBuf, scans, spans) follows ctx.stream.
+struct StreamSwap {
+  Ctx& c;
+  cudaStream_t saved;
+  StreamSwap(Ctx& ctx, cudaStream_t s) : c(ctx), saved(ctx.stream) { c.stream = s; }
+  ~StreamSwap() { c.stream = saved; }
 };
 
 // RAII device array bound to a context's stream-ordered pool.

@@ -489,32 +489,57 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
   const size_t L = (size_t)1 << cbits, R = (size_t)1 << rbits;
   DBuf<XYZZ<Fq>> buckets(cx, (size_t)nj * B);
   {
-    // sort + accumulate, one job after the other (both saturate the chip)
+    // Software pipeline over the jobs: the counting sort of job j + 1 (memory / atomic bound, ~40 registers per
+    // thread) runs on the side stream while job j's bucket pass (integer-ALU bound, 2 CTAs/SM) runs on the main
+    // stream; sort buffers are double-buffered and the two streams are chained with events.
     const size_t max_refs = (size_t)W * max_n;
     const size_t max_threads = (max_refs + MSM_Q_MIN - 1) / MSM_Q_MIN + 256;  // launches round up to whole blocks
-    DBuf<uint32_t> digits(cx, max_refs), hist(cx, B), offsets(cx, B), cursor(cx, B);
-    DBuf<uint2> sorted(cx, max_refs);
-    DBuf<uint32_t> total(cx, 1), part_bkt(cx, 2 * max_threads), n_long(cx, 2);  // n_long[0]: long runs, [1]: giant runs
+    DBuf<uint32_t> digits[2], hist[2], offsets[2], cursor[2], total[2];
+    DBuf<uint2> sorted[2];
+    const int slots = nj > 1 ? 2 : 1;
+    for (int s = 0; s < slots; s++) {
+      digits[s] = DBuf<uint32_t>(cx, max_refs); hist[s] = DBuf<uint32_t>(cx, B); offsets[s] = DBuf<uint32_t>(cx, B);
+      cursor[s] = DBuf<uint32_t>(cx, B); total[s] = DBuf<uint32_t>(cx, 1); sorted[s] = DBuf<uint2>(cx, max_refs);
+    }
+    DBuf<uint32_t> part_bkt(cx, 2 * max_threads), n_long(cx, 2);  // n_long[0]: long runs, [1]: giant runs
     const uint32_t long_cap = 1u << 18;
     DBuf<MsmLongRun> long_runs(cx, long_cap), giant_runs(cx, long_cap);
     DBuf<XYZZ<Fq>> part_pt(cx, 2 * max_threads);
     buckets.zero();  // empty buckets are never written: all-zero XYZZ is the point at infinity
+    cudaEvent_t ev_ready, ev_sorted[MSM_MAX_BATCH], ev_acc[MSM_MAX_BATCH];
+    B2M_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+    for (int j = 0; j < nj; j++) {
+      B2M_CUDA(cudaEventCreateWithFlags(&ev_sorted[j], cudaEventDisableTiming));
+      B2M_CUDA(cudaEventCreateWithFlags(&ev_acc[j], cudaEventDisableTiming));
+    }
+    B2M_CUDA(cudaEventRecord(ev_ready, cx.stream));  // buffers exist (stream-ordered allocation) and inputs are final
+    B2M_CUDA(cudaStreamWaitEvent(cx.side, ev_ready, 0));
     for (int j = 0; j < nj; j++) {
       const size_t n = jobs[j].n, nt = jobs[j].n + jobs[j].n2;
-      if (nt == 0) continue;
-      hist.zero();
-      size_t sp0 = cx.span_begin("msm_sort", (double)n);
-      msm_digits_kernel<Fr><<<div_up(nt, 256), 256, 0, cx.stream>>>(jobs[j].scalars, jobs[j].scalars2, jobs[j].mont, n, nt, c, W, digits.p,
-                                                                    hist.p);
-      B2M_CHECK_LAUNCH();
-      exclusive_scan_u32(cx, hist.p, offsets.p, B);
-      B2M_CUDA(cudaMemcpyAsync(cursor.p, offsets.p, B * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
-      msm_scatter_kernel<<<div_up(nt, 256), 256, 0, cx.stream>>>(digits.p, n, nt, jobs[j].base_off, n_srs + jobs[j].extra_base, W, cursor.p,
-                                                                  sorted.p);
-      msm_total_kernel<<<1, 1, 0, cx.stream>>>(cursor.p, B, total.p);
-      B2M_CHECK_LAUNCH();
-      cx.launches += 3;
-      cx.span_end(sp0);
+      const int s = j % slots;
+      if (nt == 0) {
+        B2M_CUDA(cudaEventRecord(ev_acc[j], cx.stream));
+        continue;
+      }
+      {
+        StreamSwap on_side(cx, cx.side);
+        if (j >= slots) B2M_CUDA(cudaStreamWaitEvent(cx.side, ev_acc[j - slots], 0));  // the slot's previous user is done
+        hist[s].zero();
+        size_t sp0 = cx.span_begin("msm_sort", (double)n);
+        msm_digits_kernel<Fr><<<div_up(nt, 256), 256, 0, cx.stream>>>(jobs[j].scalars, jobs[j].scalars2, jobs[j].mont, n, nt, c, W,
+                                                                      digits[s].p, hist[s].p);
+        B2M_CHECK_LAUNCH();
+        exclusive_scan_u32(cx, hist[s].p, offsets[s].p, B);
+        B2M_CUDA(cudaMemcpyAsync(cursor[s].p, offsets[s].p, B * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
+        msm_scatter_kernel<<<div_up(nt, 256), 256, 0, cx.stream>>>(digits[s].p, n, nt, jobs[j].base_off, n_srs + jobs[j].extra_base, W,
+                                                                    cursor[s].p, sorted[s].p);
+        msm_total_kernel<<<1, 1, 0, cx.stream>>>(cursor[s].p, B, total[s].p);
+        B2M_CHECK_LAUNCH();
+        cx.launches += 3;
+        cx.span_end(sp0);
+        B2M_CUDA(cudaEventRecord(ev_sorted[j], cx.side));
+      }
+      B2M_CUDA(cudaStreamWaitEvent(cx.stream, ev_sorted[j], 0));
       size_t sp = cx.span_begin("msm_accumulate_kernel", (double)n);
       // References per thread: near MSM_Q, chosen so that the grid is a whole number of waves of
       // (SMs x resident CTAs) -- every thread does the same work, so a partial last wave is pure loss.
@@ -525,14 +550,15 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       uint32_t q = (uint32_t)((refs + waves * wave - 1) / (waves * wave));
       if (q < (uint32_t)MSM_Q_MIN) q = MSM_Q_MIN;
       const size_t nthreads = (refs + q - 1) / q;
-      msm_accumulate_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(tables.p, stride, offsets.p, cursor.p, sorted.p, total.p, q,
-                                                                               buckets.p + (size_t)j * B, part_pt.p, part_bkt.p);
+      msm_accumulate_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(tables.p, stride, offsets[s].p, cursor[s].p, sorted[s].p,
+                                                                               total[s].p, q, buckets.p + (size_t)j * B, part_pt.p,
+                                                                               part_bkt.p);
       B2M_CHECK_LAUNCH();
       cx.launches++;
       cx.span_end(sp);
       size_t sp1 = cx.span_begin("msm_stitch", (double)n);
       n_long.zero();
-      msm_stitch_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, nthreads, q, offsets.p, cursor.p,
+      msm_stitch_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, nthreads, q, offsets[s].p, cursor[s].p,
                                                                            buckets.p + (size_t)j * B, long_runs.p, n_long.p, long_cap);
       msm_stitch_long_kernel<Fq><<<2 * cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, long_runs.p, n_long.p, long_cap,
                                                                          buckets.p + (size_t)j * B, giant_runs.p, n_long.p + 1);
@@ -541,6 +567,12 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       B2M_CHECK_LAUNCH();
       cx.launches += 3;
       cx.span_end(sp1);
+      B2M_CUDA(cudaEventRecord(ev_acc[j], cx.stream));
+    }
+    cudaEventDestroy(ev_ready);
+    for (int j = 0; j < nj; j++) {
+      cudaEventDestroy(ev_sorted[j]);
+      cudaEventDestroy(ev_acc[j]);
     }
   }
   double units = 0;
