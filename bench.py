@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--curve", default="bls12_381", choices=["bls12_381", "bn254"])
     ap.add_argument("--cpu-log-n", type=int, default=16, help="instance size of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--window-bits", type=int, default=0, help="MSM window override (0: chosen from the per-rank MSM size)")
     return ap.parse_args()
 
 
@@ -164,7 +165,8 @@ def main():
     a, b = 0x1234567890abcdef1234567890abcdef, 0xfedcba0987654321fedcba0987654321
     circ = r1cs.dummy_circuit(cid, a, b, 10, n)
     t0 = time.time()
-    srs = m.universal_setup(n, n, 3 * n, beta=0x5eed5eed5eed5eed5eed5eed, gamma=7, degree_bounds=(n - 2, 4 * n - 2))
+    srs = m.universal_setup(n, n, 3 * n, beta=0x5eed5eed5eed5eed5eed5eed, gamma=7, degree_bounds=(n - 2, 4 * n - 2),
+                            window_bits=args.window_bits)
     pk = m.index(srs, circ)
     setup_s = time.time() - t0
     m.stage(pk, circ)
@@ -209,6 +211,10 @@ def main():
     barrier()
     wall_e2e = time.perf_counter() - t0
     clocks.close()
+    # outside every timed region: a proof from a fresh zk stream, hashed, so that runs with different window sizes,
+    # GPU counts or library builds can be compared byte for byte
+    import hashlib
+    proof_sha = hashlib.sha256(m.prove(pk, circ, api.ZkRng())).hexdigest()
 
     ms_step = sum(dev_ms) / len(dev_ms)
     if dist is not None:  # max over ranks
@@ -265,7 +271,7 @@ def main():
                              "peak": alu_peak, "frac": (acc["units"] * msm_windows / (acc["ms"] / 1e3) / 1e9 / alu_peak) if acc["ms"] and alu_peak else None,
                              "peak_source": "tools/microbench.cu g1_madd (measured on this pool's B200)"},
         "msm_accumulate_ms_per_step": acc["ms"] / args.steps if acc["ms"] else None,
-        "kernels": kern, "phases_ms": phases, "dev_ms_steps": dev_ms, "setup_s": setup_s, "proof_bytes": len(proof),
+        "kernels": kern, "phases_ms": phases, "dev_ms_steps": dev_ms, "setup_s": setup_s, "proof_bytes": len(proof), "proof_sha256": proof_sha,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -44,12 +44,6 @@ struct NcclApi {
     }                                                                                                            \
   } while (0)
 
-// [lo, hi) of n items owned by `rank` of `world` (same rule as marlin_b200/multi.py shard_range)
-inline void shard_range(size_t n, int rank, int world, size_t* lo, size_t* hi) {
-  *lo = n * (size_t)rank / (size_t)world;
-  *hi = n * (size_t)(rank + 1) / (size_t)world;
-}
-
 inline void all_gather_bytes(Ctx& cx, const void* send, void* recv, size_t bytes_per_rank) {
   B2M_NCCL(NcclApi::get().AllGather(send, recv, bytes_per_rank, ncclUint8, static_cast<ncclComm_t>(cx.comm), cx.stream));
 }

@@ -42,17 +42,20 @@ struct MsmJob {
   int n_extra;
   XYZZ<Fq>* out_xyzz;      // either output may be null
   Affine<Fq>* out_affine;
+  size_t scalar_stride = 1;  // scalars[i * scalar_stride] pairs with powers[base_off + i] (multi-GPU: the rank's residue class)
 };
 
 template <class Fr, class Fq>
 struct Msm {
   Ctx* ctx;
-  size_t n_srs = 0;    // number of G1 powers
+  size_t n_srs = 0;    // G1 powers resident on THIS GPU (multi-GPU: the powers i = rank mod world, slot i / world)
+  size_t n_srs_global = 0;  // powers of the whole key
+  int tab_rank = 0, tab_world = 1;  // the communicator layout the tables were built for
   size_t n_extra = 0;  // further fixed bases (powers_of_gamma_g) appended after them
   size_t stride = 0;   // n_srs + n_extra: entries per window table
   int c = 0, W = 0;
   int acc_ctas_per_sm = 3;  // resident CTAs of msm_accumulate_kernel per SM (occupancy query)
-  DBuf<Affine<Fq>> tables;  // [W][stride]:  tables[w * stride + i] = 2^(c*w) * P_i
+  DBuf<Affine<Fq>> tables;  // [W][stride]:  tables[w * stride + k] = 2^(c*w) * P_(k * world + rank)
 
   static int pick_window(size_t n);
   // Upload the powers and build the window tables (key-load time).

@@ -61,16 +61,24 @@ __global__ void msm_precompute_kernel(Affine<Fq>* tables, size_t n, int c, int W
   }
 }
 
+// Multi-GPU key load: keep the powers of this rank's residue class, tables[k] = all[k * world + rank].
+template <class Fq>
+__global__ void msm_take_residue_kernel(const Affine<Fq>* all, size_t n_loc, int rank, int world, Affine<Fq>* tables) {
+  size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (k >= n_loc) return;
+  st_words(tables + k, ld_affine(all + k * (size_t)world + rank));
+}
+
 // ---- 1. digits ----------------------------------------------------------------------------
 // digits[w * nt + i] = (|d| - 1) | sign << 31, or MSM_NO_DIGIT for d == 0; hist[|d| - 1]++.
 // Scalars come in two groups: i < n from `scalars` (the polynomial), the rest from `scalars2`
 // (the few blinding coefficients that multiply the gamma powers), nt = n + n2.
 template <class Fr>
-__global__ void msm_digits_kernel(const Fr* scalars, const Fr* scalars2, bool MONT, size_t n, size_t nt, int c, int W, uint32_t* digits,
-                                  uint32_t* hist) {
+__global__ void msm_digits_kernel(const Fr* scalars, size_t sstride, const Fr* scalars2, bool MONT, size_t n, size_t nt, int c, int W,
+                                  uint32_t* digits, uint32_t* hist) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= nt) return;
-  Fr s = i < n ? ld_fr(scalars + i) : ld_fr(scalars2 + (i - n));
+  Fr s = i < n ? ld_fr(scalars + i * sstride) : ld_fr(scalars2 + (i - n));
   if (MONT) s = s.to_canonical();
   const uint32_t half = 1u << (c - 1);
   uint32_t carry = 0;
@@ -405,18 +413,34 @@ int Msm<Fr, Fq>::pick_window(size_t n) {
 
 template <class Fr, class Fq>
 Msm<Fr, Fq>::Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, const Affine<Fq>* host_extra, size_t n_extra_bases, int window_bits)
-    : ctx(&cx), n_srs(n), n_extra(n_extra_bases), stride(n + n_extra_bases) {
+    : ctx(&cx), n_extra(n_extra_bases), n_srs_global(n) {
+  // Multi-GPU: GPU r keeps only the powers i = r (mod world) -- every contiguous slice of the key, whatever its
+  // offset and length, then splits evenly over the GPUs, and table memory and build time drop by `world`.
+  tab_world = cx.world > 1 ? cx.world : 1;
+  tab_rank = cx.world > 1 ? cx.rank : 0;
+  n_srs = n > (size_t)tab_rank ? (n - tab_rank + tab_world - 1) / tab_world : 0;
+  stride = n_srs + n_extra;
   B2M_REQUIRE(n >= 1 && stride < ((size_t)1 << 31), B2M_ERR_INVALID_ARG, "SRS size %zu out of range", n);
-  c = window_bits > 0 ? window_bits : pick_window(n / (size_t)(cx.world > 0 ? cx.world : 1));  // sharded MSMs see n / world pairs per rank
+  c = window_bits > 0 ? window_bits : pick_window(n / (size_t)tab_world);  // sharded MSMs see n / world pairs per rank
   B2M_REQUIRE(c >= MSM_MIN_WINDOW && c <= 24, B2M_ERR_INVALID_ARG, "window bits %d out of range [%d, 24]", c, MSM_MIN_WINDOW);
   W = (Fr::Params::BITS + 1 + c - 1) / c;
   B2M_REQUIRE(W <= 32, B2M_ERR_INVALID_ARG, "too many windows (%d)", W);
   tables = DBuf<Affine<Fq>>(cx, (size_t)W * stride);
-  tables.upload(host_powers, n);
-  if (n_extra) B2M_CUDA(cudaMemcpyAsync(tables.p + n, host_extra, n_extra * sizeof(Affine<Fq>), cudaMemcpyHostToDevice, cx.stream));
-  msm_precompute_kernel<Fq><<<div_up(stride, 128), 128, 0, cx.stream>>>(tables.p, stride, c, W);
-  B2M_CHECK_LAUNCH();
-  cx.launches++;
+  if (tab_world == 1) {
+    tables.upload(host_powers, n);
+  } else if (n_srs) {
+    DBuf<Affine<Fq>> all(cx, n);
+    all.upload(host_powers, n);
+    msm_take_residue_kernel<Fq><<<div_up(n_srs, 256), 256, 0, cx.stream>>>(all.p, n_srs, tab_rank, tab_world, tables.p);
+    B2M_CHECK_LAUNCH();
+    cx.launches++;
+  }
+  if (n_extra) B2M_CUDA(cudaMemcpyAsync(tables.p + n_srs, host_extra, n_extra * sizeof(Affine<Fq>), cudaMemcpyHostToDevice, cx.stream));
+  if (stride) {  // (a rank can own none of a tiny key's powers)
+    msm_precompute_kernel<Fq><<<div_up(stride, 128), 128, 0, cx.stream>>>(tables.p, stride, c, W);
+    B2M_CHECK_LAUNCH();
+    cx.launches++;
+  }
   cx.sync();
   B2M_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas_per_sm, msm_accumulate_kernel<Fq>, 128, 0));
   if (acc_ctas_per_sm < 1) acc_ctas_per_sm = 1;
@@ -433,11 +457,14 @@ template <class Fr, class Fq>
 void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
   Ctx& cx = *ctx;
   B2M_REQUIRE(nj >= 1 && nj <= MSM_MAX_BATCH, B2M_ERR_INVALID_ARG, "MSM batch of %d jobs", nj);
-  // Multi-GPU (comm.cuh): every rank holds the full window tables and the full scalar vectors (the prover
-  // runs replicated); rank r takes the r-th contiguous chunk of every MSM's (base, scalar) pairs, reduces
-  // it to one XYZZ point, and one all-gather of 192 B per MSM per rank exchanges the partial sums.
+  // Multi-GPU (comm.cuh): the prover runs replicated, so every rank holds the full scalar vectors, but only the
+  // window tables of the powers i = rank (mod world).  Rank r takes the pairs of its residue class out of every
+  // MSM (a strided read of the scalars, a contiguous run of table slots), reduces them to one XYZZ point, and
+  // one all-gather of 192 B per MSM per rank exchanges the partial sums.
   MsmJob<Fr, Fq> local[MSM_MAX_BATCH];
   const bool sharded = cx.world > 1;
+  B2M_REQUIRE((sharded ? cx.world : 1) == tab_world && (sharded ? cx.rank : 0) == tab_rank, B2M_ERR_INVALID_ARG,
+              "this key's tables were built for rank %d of %d; create the SRS after b2m_ctx_attach_comm", tab_rank, tab_world);
   DBuf<XYZZ<Fq>> partial, gathered;
   if (sharded) {
     partial = DBuf<XYZZ<Fq>>(cx, nj);
@@ -445,12 +472,17 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
   }
   for (int j = 0; j < nj; j++) {
     local[j] = jobs_in[j];
+    B2M_REQUIRE(jobs_in[j].base_off + jobs_in[j].n <= n_srs_global, B2M_ERR_DEGREE_TOO_LARGE,
+                "MSM slice [%zu, %zu) exceeds the SRS (%zu powers)", jobs_in[j].base_off, jobs_in[j].base_off + jobs_in[j].n, n_srs_global);
     if (sharded) {
-      size_t lo, hi;
-      shard_range(jobs_in[j].n, cx.rank, cx.world, &lo, &hi);
-      local[j].scalars = jobs_in[j].scalars + lo;
-      local[j].base_off = jobs_in[j].base_off + lo;
-      local[j].n = hi - lo;
+      // pairs i of the slice with base_off + i = rank (mod world): first one at i = skip, then every world-th
+      const size_t G = (size_t)cx.world, off = jobs_in[j].base_off, n = jobs_in[j].n;
+      const size_t skip = ((size_t)cx.rank + G - off % G) % G;
+      const size_t cnt = n > skip ? (n - skip + G - 1) / G : 0;
+      local[j].scalars = jobs_in[j].scalars + skip;
+      local[j].scalar_stride = G;
+      local[j].base_off = (off + skip) / G;  // table slot of power off + skip = slot * world + rank
+      local[j].n = cnt;
       if (cx.rank != 0) { local[j].scalars2 = nullptr; local[j].n2 = 0; }  // the blinding terms go to rank 0
       local[j].extra = nullptr; local[j].n_extra = 0;
       local[j].out_xyzz = partial.p + j; local[j].out_affine = nullptr;
@@ -459,7 +491,7 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
   const MsmJob<Fr, Fq>* jobs = local;
   size_t max_n = 0;
   for (int j = 0; j < nj; j++) {
-    B2M_REQUIRE(jobs[j].base_off + jobs[j].n <= n_srs, B2M_ERR_DEGREE_TOO_LARGE, "MSM slice [%zu, %zu) exceeds the SRS (%zu powers)",
+    B2M_REQUIRE(jobs[j].n == 0 || jobs[j].base_off + jobs[j].n <= n_srs, B2M_ERR_DEGREE_TOO_LARGE, "MSM slot range [%zu, %zu) exceeds the tables (%zu)",
                 jobs[j].base_off, jobs[j].base_off + jobs[j].n, n_srs);
     B2M_REQUIRE(jobs[j].n2 == 0 || jobs[j].extra_base + jobs[j].n2 <= n_extra, B2M_ERR_INVALID_ARG, "extra bases out of range");
     max_n = std::max(max_n, jobs[j].n + jobs[j].n2);
@@ -526,7 +558,7 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
         if (j >= slots) B2M_CUDA(cudaStreamWaitEvent(cx.side, ev_acc[j - slots], 0));  // the slot's previous user is done
         hist[s].zero();
         size_t sp0 = cx.span_begin("msm_sort", (double)n);
-        msm_digits_kernel<Fr><<<div_up(nt, 256), 256, 0, cx.stream>>>(jobs[j].scalars, jobs[j].scalars2, jobs[j].mont, n, nt, c, W,
+        msm_digits_kernel<Fr><<<div_up(nt, 256), 256, 0, cx.stream>>>(jobs[j].scalars, jobs[j].scalar_stride, jobs[j].scalars2, jobs[j].mont, n, nt, c, W,
                                                                       digits[s].p, hist[s].p);
         B2M_CHECK_LAUNCH();
         exclusive_scan_u32(cx, hist[s].p, offsets[s].p, B);

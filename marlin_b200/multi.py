@@ -1,4 +1,4 @@
-"""Multi-GPU plumbing: one process per GPU (torchrun), MSMs sharded by (base, scalar) chunk with one
+"""Multi-GPU plumbing: one process per GPU (torchrun), MSMs sharded by residue class of the SRS index with one
 NCCL all-gather of partial sums per MSM batch (include/b2m.h b2m_ctx_attach_comm).  torch.distributed is
 used only to hand the NCCL unique id from rank 0 to the other ranks."""
 import ctypes
@@ -8,9 +8,19 @@ from . import _lib
 UNIQUE_ID_BYTES = 128
 
 
-def shard_range(n, rank, world):
-    """[lo, hi) of n (base, scalar) pairs owned by `rank` -- the rule csrc/comm.cuh shard_range applies."""
-    return n * rank // world, n * (rank + 1) // world
+def shard_slots(base_off, n, rank, world):
+    """The pairs of the MSM slice powers[base_off : base_off + n] that GPU `rank` computes -- the rule of
+    csrc/msm_impl.cuh run_batch.  GPU r holds the window tables of the powers i = r (mod world) at slot i // world,
+    so it takes the pairs with base_off + i = r (mod world).
+    Returns (skip, count, first_slot): pairs i = skip + k * world for k < count; pair i uses table slot first_slot + k."""
+    skip = (rank - base_off) % world
+    count = (n - skip + world - 1) // world if n > skip else 0
+    return skip, count, (base_off + skip) // world
+
+
+def resident_powers(n_srs, rank, world):
+    """number of SRS powers whose window tables live on GPU `rank`"""
+    return (n_srs - rank + world - 1) // world if n_srs > rank else 0
 
 
 def broadcast_unique_id(dist, rank, make_id, device=None):

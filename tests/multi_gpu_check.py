@@ -39,6 +39,24 @@ def main():
         print(f"rank {rank}/{world} {scheme}: {'OK' if good else 'MISMATCH'}", flush=True)
         ok = ok and good
         pk.close(); srs.close()
+    # level 0: slices of every offset / length parity through the residue-class shard rule (b2m_srs_msm)
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import b2m_testutil as tu
+    m = api.Marlin("bls12_381", "marlin_kzg10", device=local)
+    multi.attach(m.ctx, dist, rank, world)
+    beta, n_srs = 0xabcdef12345, 1000
+    srs = m.srs_from_trapdoor(n_srs - 1, beta=beta, gamma=7)
+    rnd = random.Random(5)
+    for off, cnt in ((0, n_srs), (1, 1), (3, 2), (7, world), (11, world + 1), (999, 1), (0, 0), (13, 500), (world - 1, 64)):
+        sc = [rnd.randrange(f.p) for _ in range(cnt)]
+        got = tu.srs_msm(srs.handle, curve, off, sc)
+        good = got == tu.trapdoor_msm(curve, curve.g, beta, off, sc)
+        if not good:
+            print(f"rank {rank}/{world} srs_msm off={off} n={cnt}: MISMATCH", flush=True)
+        ok = ok and good
+    print(f"rank {rank}/{world} level-0 slices: {'OK' if ok else 'MISMATCH'}", flush=True)
+    srs.close()
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -26,12 +26,18 @@ def _worker(rank, world, port, n, q):
         scalars = [rnd.randrange(curve.fr.p) for _ in range(n)]
         blind_bases = [ec.scalar_mul(curve, 11 + i, curve.g) for i in range(3)]
         blind = [rnd.randrange(curve.fr.p) for _ in range(3)]
-        lo, hi = multi.shard_range(n, rank, world)
-        part = ec.msm_naive(curve, bases[lo:hi], scalars[lo:hi])
+        # the MSM is the slice powers[off : off + n] of a longer key; this rank holds the powers = rank (mod world)
+        off = 5
+        skip, cnt, slot0 = multi.shard_slots(off, n, rank, world)
+        key = [None] * off + bases
+        resident = key[rank::world]  # slot k <-> power k * world + rank
+        mine = [skip + k * world for k in range(cnt)]
+        assert all(resident[slot0 + k] is key[off + i] for k, i in enumerate(mine))
+        part = ec.msm_naive(curve, [bases[i] for i in mine], [scalars[i] for i in mine])
         if rank == 0:  # the blinding terms ride with rank 0's shard
             part = ec.affine_add(curve, part, ec.msm_naive(curve, blind_bases, blind))
         gathered = [None] * world
-        dist.all_gather_object(gathered, (lo, hi, part))
+        dist.all_gather_object(gathered, (skip, cnt, part))
         total = None
         for _, _, p in gathered:
             total = ec.affine_add(curve, total, p)
@@ -56,15 +62,28 @@ def test_sharded_msm_world2(n):
         assert p.exitcode == 0
     uids = {r[1] for r in res}
     assert len(uids) == 1 and len(next(iter(uids))) == multi.UNIQUE_ID_BYTES
-    for _, _, ranges, ok in res:
+    for _, _, parts, ok in res:
         assert ok
-        assert ranges[0][0] == 0 and ranges[-1][1] == n and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        assert sum(cnt for _, cnt in parts) == n
 
 
-def test_shard_range_partitions():
-    for n in (0, 1, 5, 1 << 20, (1 << 22) - 1):
+def test_shard_slots_partition():
+    """every pair of every slice is taken by exactly one rank, evenly, and lands inside that rank's tables"""
+    for n_srs in (1, 5, 64, 1000):
         for world in (1, 2, 4, 8):
-            parts = [multi.shard_range(n, r, world) for r in range(world)]
-            assert parts[0][0] == 0 and parts[-1][1] == n
-            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
-            assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
+            for off in (0, 1, 3, n_srs // 2):
+                for n in (0, 1, 5, n_srs - off):
+                    if n < 0 or off + n > n_srs:
+                        continue
+                    seen, counts = [], []
+                    for r in range(world):
+                        skip, cnt, slot0 = multi.shard_slots(off, n, r, world)
+                        counts.append(cnt)
+                        for k in range(cnt):
+                            i = skip + k * world
+                            assert (off + i) % world == r and (off + i) // world == slot0 + k
+                            assert slot0 + k < multi.resident_powers(n_srs, r, world)
+                            seen.append(i)
+                    assert sorted(seen) == list(range(n))
+                    assert max(counts) - min(counts) <= 1
+            assert sum(multi.resident_powers(n_srs, r, world) for r in range(world)) == n_srs
