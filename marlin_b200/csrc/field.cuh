@@ -270,6 +270,101 @@ struct Fp {
     for (int i = 0; i < N; i++) e[i] = P::pm2(i);
     return pow_limbs(e, N);
   }
+  // Inverse by the binary extended Euclid (Kaliski's almost-inverse, shifts batched by trailing-zero count):
+  // ~270 subtract-and-shift steps of plain limb adds / shifts -- an order of magnitude fewer issue slots than
+  // the Fermat ladder and none of them on the multiplier pipe, so in a kernel whose other warps are busy
+  // multiplying it is nearly free.  Data-dependent trip count (NOT constant time; nothing here is secret to
+  // the GPU).  inverse_fast(0) = 0.
+  B2M_HD Fp inverse_fast() const {
+    if (is_zero()) return *this;
+    // With x = the limbs of *this read as an integer, the loop keeps (mod p)
+    //   x * ra = -sg * a * 2^k,   x * rb = sg * b * 2^k,   a * rb + b * ra = p   (so ra, rb <= p: no overflow)
+    // and ends with a == b == gcd = 1, i.e. x^-1 * 2^k = sg * rb.
+    uint32_t a[N], b[N], ra[N], rb[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      a[i] = P::mod(i);
+      b[i] = l[i];
+      ra[i] = 0;
+      rb[i] = 0;
+    }
+    rb[0] = 1;
+    uint32_t k = 0;
+    bool negate = false;
+    while (!(b[0] & 1u)) {  // x even: halve b (ra = 0 needs no doubling)
+      uint32_t z = b[0] ? ctz32(b[0]) : 31u;
+      shr_limbs(b, z);
+      k += z;
+    }
+    for (;;) {
+      // a, b odd
+      uint32_t t[N];
+      t[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+      for (int i = 1; i < N; i++) t[i] = subc_cc(a[i], b[i]);
+      uint32_t borrow = subc(0u, 0u);
+      uint32_t nz = 0;
+#pragma unroll
+      for (int i = 0; i < N; i++) nz |= t[i];
+      if (nz == 0) break;
+      if (borrow) {  // a < b: swap the two (value, cofactor) pairs, flip the sign
+        negate = !negate;
+        uint32_t c = 1u;  // a <- b - a = -t
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          uint32_t v = ~t[i] + c;
+          c = (c && v == 0) ? 1u : 0u;
+          t[i] = v;
+          uint32_t w = ra[i];
+          ra[i] = rb[i];
+          rb[i] = w;
+          b[i] = a[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < N; i++) a[i] = t[i];
+      ra[0] = add_cc(ra[0], rb[0]);
+#pragma unroll
+      for (int i = 1; i < N - 1; i++) ra[i] = addc_cc(ra[i], rb[i]);
+      ra[N - 1] = addc(ra[N - 1], rb[N - 1]);
+      do {  // a even and non-zero
+        uint32_t z = a[0] ? ctz32(a[0]) : 31u;
+        shr_limbs(a, z);
+        shl_limbs(rb, z);
+        k += z;
+      } while (!(a[0] & 1u));
+    }
+    Fp y;
+#pragma unroll
+    for (int i = 0; i < N; i++) y.l[i] = rb[i];
+    if (negate) y = modulus_raw_sub(y);
+    // y = x^-1 * 2^k with x = v * R  =>  v^-1 * R = x^-1 * R^2 = y * 2^(64 N - k)
+    uint32_t e = 64u * N - k;
+    uint32_t extra = e > 32u * N - 1 ? e - (32u * N - 1) : 0u;
+    e -= extra;
+    Fp pw = zero();
+    pw.l[e >> 5] = 1u << (e & 31u);
+    y = (y * r2()) * pw;  // (y * R) * 2^e / R
+    for (uint32_t i = 0; i < extra; i++) y = y.dbl();
+    return y;
+  }
+  B2M_HD static uint32_t ctz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)(__ffs((int)v) - 1);
+#else
+    return (uint32_t)__builtin_ctz(v);
+#endif
+  }
+  B2M_HD static void shr_limbs(uint32_t* v, uint32_t z) {  // 1 <= z <= 31
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) v[i] = (v[i] >> z) | (v[i + 1] << (32u - z));
+    v[N - 1] >>= z;
+  }
+  B2M_HD static void shl_limbs(uint32_t* v, uint32_t z) {  // 1 <= z <= 31
+#pragma unroll
+    for (int i = N - 1; i > 0; i--) v[i] = (v[i] << z) | (v[i - 1] >> (32u - z));
+    v[0] <<= z;
+  }
   // canonical value > (p-1)/2 ?  (`self > -self` in ark-ec's y-sign flag)  -- input is canonical.
   B2M_HD bool canonical_gt_half() const {
     for (int i = N - 1; i >= 0; i--) {

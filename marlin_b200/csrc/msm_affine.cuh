@@ -1,0 +1,286 @@
+// Batched-affine bucket levels for the MSM (csrc/msm_impl.cuh run_batch).
+//
+// The references of one MSM are sorted by bucket.  Level l holds cnt_l[b] affine points of bucket b at
+// positions [off_l[b], off_l[b + 1]); level 0 is the sorted reference list itself (points = +-table entries).
+// One level adds the points of every bucket in pairs: cnt_(l+1)[b] = ceil(cnt_l[b] / 2), output j of bucket b
+// = point 2j + point 2j + 1 (or a copy of point 2j when the count is odd).  All additions of a level are
+// independent, so they are done in AFFINE coordinates with the slopes' denominators inverted together
+// (Montgomery's trick): 6 field multiplications per addition instead of 10 for an XYZZ mixed addition.
+// A light plan pass resolves which two points make each output.  A thread then owns T consecutive outputs: pass 1 multiplies the denominators up (prefix products to a scratch
+// array), one binary-Euclid inversion (field.cuh inverse_fast: adds and shifts only, it runs on the ALU pipe
+// while other warps multiply), pass 2 walks back and writes the sums.  After a few levels the remaining points
+// (n / 2^levels) go through the XYZZ bucket pass, which balances any bucket-size distribution.
+//
+// Host/device shared: tests/host builds this with g++ (carry flag emulated) and checks it against the oracle.
+#pragma once
+#include "curve.cuh"
+#ifdef __CUDACC__
+#include "devmem.cuh"
+#else
+struct uint2 {
+  uint32_t x, y;
+};
+struct uint4 {
+  uint32_t x, y, z, w;
+};
+#endif
+
+namespace b2m {
+
+constexpr uint32_t AFF_BKT_BITS = 24;  // == MSM_BKT_BITS (msm.cuh): reference = {table index | sign << 31, bucket | window << 24}
+
+template <class Fq>
+struct AffLevel {
+  // level-0 source: position i is the point +-tables[window * table_stride + index] named by sorted[i]
+  const Affine<Fq>* tables;
+  size_t table_stride;
+  const uint2* sorted;
+  // level >= 1 source: position i is in[i]
+  const Affine<Fq>* in;
+  const uint32_t* off_in;   // [B + 1] bucket starts of the input level (off_in[B] = number of points)
+  const uint32_t* off_out;  // [B + 1] bucket starts of the output level
+  uint32_t B;
+  Affine<Fq>* out;
+  uint2* out_refs;  // last level only (else null): {position, bucket} references for the XYZZ pass over `out`
+  Fq* pref;         // [T][nthreads] running denominator products
+  uint4* meta;      // [T][nthreads] the plan: {P index | negate << 31, Q index | negate << 31, bucket, has Q}
+  uint32_t T, nthreads;
+};
+
+#if defined(__CUDA_ARCH__)
+#define B2M_AFF_LDG(p) ldg_words(p)
+#define B2M_AFF_LD(p) ld_words(p)
+#define B2M_AFF_ST(p, v) st_words(p, v)
+#define B2M_AFF_LDG32(p) __ldg(p)
+#else
+#define B2M_AFF_LDG(p) (*(p))
+#define B2M_AFF_LD(p) (*(p))
+#define B2M_AFF_ST(p, v) (*(p) = (v))
+#define B2M_AFF_LDG32(p) (*(p))
+#endif
+
+// first index in off[0 .. n] whose value is > v, minus one: the (non-empty) bucket holding position v
+B2M_HD uint32_t aff_bucket_of(const uint32_t* off, uint32_t n, uint32_t v) {
+  uint32_t lo = 0, hi = n;  // invariant: off[lo] <= v < off[hi]  (off[0] = 0, off[n] = total > v)
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (B2M_AFF_LDG32(off + mid) <= v) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ---- plan: which two input points make output o (a light, latency-bound pass kept out of the arithmetic kernel) ----
+// Thread t plans the outputs [t * T, t * T + T): meta[k][t] = {index of P, index of Q, bucket, has Q}; the indices
+// address `tables` (level 0, resolved from the sorted references, with the sign in bit 31) or `in` (later levels).
+template <class Fq, bool L0>
+B2M_HD void aff_plan_thread(const AffLevel<Fq>& A, uint32_t t) {
+  const uint32_t total = B2M_AFF_LDG32(A.off_out + A.B);
+  const uint64_t o0_64 = (uint64_t)t * A.T;
+  if (o0_64 >= total) return;
+  const uint32_t o0 = (uint32_t)o0_64;
+  const uint32_t cnt = total - o0 < A.T ? total - o0 : A.T;
+  uint32_t b = aff_bucket_of(A.off_out, A.B, o0);
+  uint32_t b_start = B2M_AFF_LDG32(A.off_out + b), b_end = B2M_AFF_LDG32(A.off_out + b + 1);
+  uint32_t in_start = B2M_AFF_LDG32(A.off_in + b), in_end = B2M_AFF_LDG32(A.off_in + b + 1);
+  for (uint32_t k = 0; k < cnt; k++) {
+    const uint32_t o = o0 + k;
+    while (o >= b_end) {  // next non-empty bucket
+      b++;
+      b_start = b_end;
+      b_end = B2M_AFF_LDG32(A.off_out + b + 1);
+      in_start = in_end;
+      in_end = B2M_AFF_LDG32(A.off_in + b + 1);
+    }
+    const uint32_t i0 = in_start + 2u * (o - b_start);
+    const bool pair = i0 + 1u < in_end;
+    uint4 m;
+    if (L0) {
+      const uint2 r0 = B2M_AFF_LDG32(A.sorted + i0);
+      m.x = (uint32_t)((size_t)(r0.y >> AFF_BKT_BITS) * A.table_stride + (r0.x & 0x7fffffffu)) | (r0.x & 0x80000000u);
+      m.y = m.x;
+      if (pair) {
+        const uint2 r1 = B2M_AFF_LDG32(A.sorted + i0 + 1u);
+        m.y = (uint32_t)((size_t)(r1.y >> AFF_BKT_BITS) * A.table_stride + (r1.x & 0x7fffffffu)) | (r1.x & 0x80000000u);
+      }
+    } else {
+      m.x = i0;
+      m.y = pair ? i0 + 1u : i0;
+    }
+    m.z = b;
+    m.w = pair ? 1u : 0u;
+    A.meta[(size_t)k * A.nthreads + t] = m;
+  }
+}
+
+template <class Fq>
+B2M_HD Fq aff_ldx(const Affine<Fq>* base, uint32_t ref) {
+  return B2M_AFF_LDG(&base[ref & 0x7fffffffu].x);
+}
+template <class Fq>
+B2M_HD Affine<Fq> aff_ld(const Affine<Fq>* base, uint32_t ref) {
+  const Affine<Fq>* p = base + (ref & 0x7fffffffu);
+  Affine<Fq> r;
+  r.x = B2M_AFF_LDG(&p->x);
+  r.y = B2M_AFF_LDG(&p->y);
+  return r;
+}
+template <class Fq>
+B2M_HD Affine<Fq> aff_signed(Affine<Fq> p, uint32_t ref) {
+  if (ref >> 31) p.y = p.y.neg();
+  return p;
+}
+
+enum AffKind : uint32_t { AFF_COPY_P = 0, AFF_COPY_Q = 1, AFF_INF = 2, AFF_ADD = 3, AFF_DBL = 4 };
+
+// P + Q: which formula, and the denominator of its slope (AFF_ADD / AFF_DBL only).
+template <class Fq>
+B2M_HD AffKind aff_classify(const Affine<Fq>& P, const Affine<Fq>& Q, Fq* den) {
+  if (P.is_inf()) return AFF_COPY_Q;
+  if (Q.is_inf()) return AFF_COPY_P;
+  if (P.x == Q.x) {
+    if (P.y == Q.y && !P.y.is_zero()) {
+      *den = P.y.dbl();
+      return AFF_DBL;
+    }
+    return AFF_INF;  // Q = -P (or a 2-torsion point doubled)
+  }
+  *den = Q.x - P.x;
+  return AFF_ADD;
+}
+
+// ---- arithmetic: thread t adds the planned pairs of its T outputs with one shared inversion -----------------------
+// PF: load the next iteration's operands before the current iteration's multiplications (costs ~50 registers, so
+// fewer resident warps); without it the loads are issued at use and latency is hidden by occupancy alone.  The
+// random 96-byte gathers from the multi-GB window tables make these kernels latency / DRAM-page bound, and
+// memory-level parallelism from more resident warps measured better than prefetch depth.
+template <class Fq, bool PF>
+B2M_HD void aff_level_thread(const AffLevel<Fq>& A, const Affine<Fq>* base, uint32_t t) {
+  const uint32_t total = B2M_AFF_LDG32(A.off_out + A.B);
+  const uint64_t o0_64 = (uint64_t)t * A.T;
+  if (o0_64 >= total) return;
+  const uint32_t o0 = (uint32_t)o0_64;
+  const uint32_t cnt = total - o0 < A.T ? total - o0 : A.T;
+  const size_t nth = A.nthreads;
+  const uint4* meta = A.meta + t;
+  Fq* pref = A.pref + t;
+  // ---- pass 1: denominators, running product ----------------------------------------------------
+  Fq run = Fq::one();
+  bool any = false;
+  {
+    uint4 m = meta[0];
+    uint4 m1 = cnt > 1 ? meta[nth] : m;
+    Fq x1, x2;
+    if (PF) {
+      x1 = aff_ldx(base, m.x);
+      x2 = aff_ldx(base, m.y);
+    }
+    for (uint32_t k = 0; k < cnt; k++) {
+      const uint4 mc = m;
+      Fq c1, c2;
+      if (PF) {
+        c1 = x1;
+        c2 = x2;
+      } else {
+        c1 = aff_ldx(base, mc.x);
+        c2 = aff_ldx(base, mc.y);
+      }
+      if (k + 1 < cnt) {  // the plan runs two outputs ahead, (PF) the operands one
+        m = m1;
+        if (k + 2 < cnt) m1 = meta[(size_t)(k + 2) * nth];
+        if (PF) {
+          x1 = aff_ldx(base, m.x);
+          x2 = aff_ldx(base, m.y);
+        }
+      }
+      if (mc.w) {
+        Fq den;
+        bool has = true;
+        if (c1.is_zero() || c2.is_zero() || c1 == c2) {  // rare: infinity, doubling or cancellation
+          const AffKind kind = aff_classify(aff_signed(aff_ld(base, mc.x), mc.x), aff_signed(aff_ld(base, mc.y), mc.y), &den);
+          has = kind == AFF_ADD || kind == AFF_DBL;
+        } else {
+          den = c2 - c1;
+        }
+        if (has) {
+          run = any ? run * den : den;
+          any = true;
+        }
+      }
+      B2M_AFF_ST(pref + (size_t)k * nth, run);
+    }
+  }
+  // ---- one inversion per thread -------------------------------------------------------------------
+  Fq inv = any ? run.inverse_fast() : run;
+  // ---- pass 2: walk back, peel one denominator at a time ----------------------------------------------
+  {
+    uint4 m = meta[(size_t)(cnt - 1) * nth];
+    uint4 m1 = cnt > 1 ? meta[(size_t)(cnt - 2) * nth] : m;
+    Affine<Fq> Pn, Qn;
+    Fq pfn = run;  // product of the denominators before the output (read for k > 0 only)
+    if (PF) {
+      Pn = aff_ld(base, m.x);
+      Qn = aff_ld(base, m.y);
+      if (cnt > 1) pfn = B2M_AFF_LD(pref + (size_t)(cnt - 2) * nth);
+    }
+    for (uint32_t k = cnt; k-- > 0;) {
+      const uint4 mc = m;
+      Affine<Fq> P, Q;
+      Fq pf = run;
+      if (PF) {
+        P = Pn;
+        Q = Qn;
+        pf = pfn;
+      } else {
+        P = aff_ld(base, mc.x);
+        Q = aff_ld(base, mc.y);
+        if (k > 0) pf = B2M_AFF_LD(pref + (size_t)(k - 1) * nth);
+      }
+      P = aff_signed(P, mc.x);
+      Q = aff_signed(Q, mc.y);
+      if (k > 0) {
+        m = m1;
+        if (k > 1) m1 = meta[(size_t)(k - 2) * nth];
+        if (PF) {
+          Pn = aff_ld(base, m.x);
+          Qn = aff_ld(base, m.y);
+          if (k > 1) pfn = B2M_AFF_LD(pref + (size_t)(k - 2) * nth);
+        }
+      }
+      Affine<Fq> R = P;
+      if (mc.w) {
+        Fq den;
+        const AffKind kind = aff_classify(P, Q, &den);
+        if (kind == AFF_COPY_Q) {
+          R = Q;
+        } else if (kind == AFF_INF) {
+          R = Affine<Fq>::inf();
+        } else if (kind != AFF_COPY_P) {
+          Fq dinv = inv;
+          if (k > 0) dinv = inv * pf;
+          inv = inv * den;
+          Fq lam;
+          if (kind == AFF_ADD) {
+            lam = (Q.y - P.y) * dinv;
+            R.x = lam.sqr() - P.x - Q.x;
+          } else {
+            const Fq xx = P.x.sqr();
+            lam = (xx.dbl() + xx) * dinv;
+            R.x = lam.sqr() - P.x.dbl();
+          }
+          R.y = lam * (P.x - R.x) - P.y;
+        }
+      }
+      const uint32_t o = o0 + k;
+      B2M_AFF_ST(&A.out[o].x, R.x);
+      B2M_AFF_ST(&A.out[o].y, R.y);
+      if (A.out_refs) {
+        uint2 r;
+        r.x = o;
+        r.y = mc.z;  // window 0: `out` is addressed directly
+        A.out_refs[o] = r;
+      }
+    }
+  }
+}
+
+}  // namespace b2m

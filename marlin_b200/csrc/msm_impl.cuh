@@ -3,6 +3,7 @@
 #include "msm.cuh"
 #include "devmem.cuh"
 #include "scan.cuh"
+#include "msm_affine.cuh"
 #include "comm.cuh"
 
 namespace b2m {
@@ -185,6 +186,24 @@ msm_accumulate_kernel(const Affine<Fq>* __restrict__ tables, size_t table_stride
   part_bkt[2 * (size_t)t] = head_b;
   part_bkt[2 * (size_t)t + 1] = tail_b;
 }
+// ---- 4a. batched-affine levels (msm_affine.cuh) ------------------------------------------------------
+// cnt[b] = ceil(points of bucket b / 2): sizes of the next level; cnt[B] = 0 so that its scan ends with the total.
+static __global__ void msm_level_counts_kernel(const uint32_t* off_in, uint32_t B, uint32_t* cnt) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > B) return;
+  cnt[b] = b < B ? (off_in[b + 1] - off_in[b] + 1u) / 2u : 0u;
+}
+template <class Fq, bool L0>
+__global__ void __launch_bounds__(256) msm_affine_plan_kernel(const AffLevel<Fq> A) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < A.nthreads) aff_plan_thread<Fq, L0>(A, t);
+}
+template <class Fq, int MINB, bool PF>
+__global__ void __launch_bounds__(128, MINB) msm_affine_level_kernel(const AffLevel<Fq> A, const Affine<Fq>* __restrict__ base) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < A.nthreads) aff_level_thread<Fq, PF>(A, base, t);
+}
+
 // Partials are ordered by bucket (they follow the sorted references).  The first partial of each bucket
 // sums the ones that follow it and stores the bucket; a bucket cut into many partials (skewed scalar
 // distributions, e.g. a polynomial whose coefficients are nearly all equal) is queued for
@@ -275,7 +294,6 @@ msm_stitch_giant_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, const
     __syncthreads();
   }
 }
-static __global__ void msm_total_kernel(const uint32_t* cursor, uint32_t B, uint32_t* total) { *total = cursor[B - 1]; }
 
 // ---- 5. reduce ----------------------------------------------------------------------------------
 // sum_b (b + 1) B_b for a BATCH of bucket arrays at once (the MSMs of one commit round), built from
@@ -444,6 +462,14 @@ Msm<Fr, Fq>::Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, const Affine<
   cx.sync();
   B2M_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas_per_sm, msm_accumulate_kernel<Fq>, 128, 0));
   if (acc_ctas_per_sm < 1) acc_ctas_per_sm = 1;
+  if (const char* e = getenv("B2M_MSM_AFFINE_LEVELS")) affine_levels = atoi(e);
+  if (const char* e = getenv("B2M_MSM_AFFINE_T")) affine_T = atoi(e);
+  if (const char* e = getenv("B2M_MSM_AFFINE_CTAS")) affine_ctas = atoi(e);
+  if (const char* e = getenv("B2M_MSM_AFFINE_MIN_REFS")) affine_min_refs = (size_t)atoll(e);
+  if (affine_levels < 0) affine_levels = 0;
+  if (affine_levels > MSM_MAX_AFFINE_LEVELS) affine_levels = MSM_MAX_AFFINE_LEVELS;
+  if (affine_T < 1) affine_T = 1;
+  if (affine_T > 1024) affine_T = 1024;
 }
 
 template <class Fr, class Fq>
@@ -526,17 +552,36 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
     // stream; sort buffers are double-buffered and the two streams are chained with events.
     const size_t max_refs = (size_t)W * max_n;
     const size_t max_threads = (max_refs + MSM_Q_MIN - 1) / MSM_Q_MIN + 256;  // launches round up to whole blocks
-    DBuf<uint32_t> digits[2], hist[2], offsets[2], cursor[2], total[2];
+    DBuf<uint32_t> digits[2], hist[2], offsets[2], cursor[2];
     DBuf<uint2> sorted[2];
     const int slots = nj > 1 ? 2 : 1;
     for (int s = 0; s < slots; s++) {
-      digits[s] = DBuf<uint32_t>(cx, max_refs); hist[s] = DBuf<uint32_t>(cx, B); offsets[s] = DBuf<uint32_t>(cx, B);
-      cursor[s] = DBuf<uint32_t>(cx, B); total[s] = DBuf<uint32_t>(cx, 1); sorted[s] = DBuf<uint2>(cx, max_refs);
+      digits[s] = DBuf<uint32_t>(cx, max_refs); hist[s] = DBuf<uint32_t>(cx, B + 1); offsets[s] = DBuf<uint32_t>(cx, B + 1);
+      cursor[s] = DBuf<uint32_t>(cx, B); sorted[s] = DBuf<uint2>(cx, max_refs);
     }
     DBuf<uint32_t> part_bkt(cx, 2 * max_threads), n_long(cx, 2);  // n_long[0]: long runs, [1]: giant runs
     const uint32_t long_cap = 1u << 18;
     DBuf<MsmLongRun> long_runs(cx, long_cap), giant_runs(cx, long_cap);
     DBuf<XYZZ<Fq>> part_pt(cx, 2 * max_threads);
+    // batched-affine levels (msm_affine.cuh): level l has at most bound[l] points
+    const int LV = max_refs >= affine_min_refs ? affine_levels : 0;  // (the largest job of the batch decides the buffers)
+    size_t bound[MSM_MAX_AFFINE_LEVELS + 1];
+    bound[0] = max_refs;
+    for (int l = 1; l <= LV; l++) bound[l] = (bound[l - 1] + B) / 2 + 1;
+    DBuf<Affine<Fq>> lvl_pts[2];
+    DBuf<uint32_t> lvl_off[2], lvl_cnt;
+    DBuf<uint2> lvl_refs;
+    DBuf<uint4> lvl_meta;
+    DBuf<Fq> lvl_pref;
+    if (LV > 0) {
+      lvl_pts[0] = DBuf<Affine<Fq>>(cx, bound[1]);
+      if (LV > 1) lvl_pts[1] = DBuf<Affine<Fq>>(cx, bound[2]);
+      lvl_off[0] = DBuf<uint32_t>(cx, B + 1); lvl_off[1] = DBuf<uint32_t>(cx, B + 1); lvl_cnt = DBuf<uint32_t>(cx, B + 1);
+      lvl_refs = DBuf<uint2>(cx, bound[LV]);
+      const size_t slots_l0 = (size_t)affine_T * ((bound[1] + affine_T - 1) / affine_T + 128);
+      lvl_meta = DBuf<uint4>(cx, slots_l0);
+      lvl_pref = DBuf<Fq>(cx, slots_l0);
+    }
     buckets.zero();  // empty buckets are never written: all-zero XYZZ is the point at infinity
     cudaEvent_t ev_ready, ev_sorted[MSM_MAX_BATCH], ev_acc[MSM_MAX_BATCH];
     B2M_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
@@ -561,36 +606,79 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
         msm_digits_kernel<Fr><<<div_up(nt, 256), 256, 0, cx.stream>>>(jobs[j].scalars, jobs[j].scalar_stride, jobs[j].scalars2, jobs[j].mont, n, nt, c, W,
                                                                       digits[s].p, hist[s].p);
         B2M_CHECK_LAUNCH();
-        exclusive_scan_u32(cx, hist[s].p, offsets[s].p, B);
+        exclusive_scan_u32(cx, hist[s].p, offsets[s].p, B + 1);  // hist[B] = 0: offsets[B] = number of references
         B2M_CUDA(cudaMemcpyAsync(cursor[s].p, offsets[s].p, B * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
         msm_scatter_kernel<<<div_up(nt, 256), 256, 0, cx.stream>>>(digits[s].p, n, nt, jobs[j].base_off, n_srs + jobs[j].extra_base, W,
                                                                     cursor[s].p, sorted[s].p);
-        msm_total_kernel<<<1, 1, 0, cx.stream>>>(cursor[s].p, B, total[s].p);
         B2M_CHECK_LAUNCH();
-        cx.launches += 3;
+        cx.launches += 2;
         cx.span_end(sp0);
         B2M_CUDA(cudaEventRecord(ev_sorted[j], cx.side));
       }
       B2M_CUDA(cudaStreamWaitEvent(cx.stream, ev_sorted[j], 0));
+      // source of the XYZZ bucket pass: the sorted references into the window tables, or -- after LV batched-affine
+      // levels -- the last level's points with one reference each
+      const Affine<Fq>* src_tables = tables.p;
+      size_t src_stride = stride;
+      const uint32_t* src_off = offsets[s].p;
+      const uint2* src_sorted = sorted[s].p;
+      size_t refs = (size_t)W * nt;  // upper bound on the reference count (zero digits are rare)
+      if (LV > 0 && refs >= affine_min_refs) {
+        size_t spl = cx.span_begin("msm_affine_levels", (double)n);
+        bound[0] = refs;
+        for (int l = 1; l <= LV; l++) bound[l] = (bound[l - 1] + B) / 2 + 1;
+        const uint32_t* off_in = offsets[s].p;
+        for (int l = 0; l < LV; l++) {
+          uint32_t* off_out = lvl_off[l & 1].p;
+          msm_level_counts_kernel<<<div_up((size_t)B + 1, 256), 256, 0, cx.stream>>>(off_in, B, lvl_cnt.p);
+          B2M_CHECK_LAUNCH();
+          cx.launches++;
+          exclusive_scan_u32(cx, lvl_cnt.p, off_out, (size_t)B + 1);
+          const uint32_t nthreads = (uint32_t)((bound[l + 1] + affine_T - 1) / affine_T);
+          AffLevel<Fq> A{tables.p, stride, sorted[s].p, l > 0 ? lvl_pts[(l - 1) & 1].p : nullptr, off_in, off_out, B, lvl_pts[l & 1].p,
+                         l == LV - 1 ? lvl_refs.p : nullptr, lvl_pref.p, lvl_meta.p, (uint32_t)affine_T, nthreads};
+          if (l == 0)
+            msm_affine_plan_kernel<Fq, true><<<div_up(nthreads, 256), 256, 0, cx.stream>>>(A);
+          else
+            msm_affine_plan_kernel<Fq, false><<<div_up(nthreads, 256), 256, 0, cx.stream>>>(A);
+          const Affine<Fq>* base = l == 0 ? tables.p : lvl_pts[(l - 1) & 1].p;
+          const unsigned grid = div_up(nthreads, 128);
+          switch (affine_ctas) {  // resident CTAs per SM the kernel is compiled for; 3 = with operand prefetch
+            case 3: msm_affine_level_kernel<Fq, 3, true><<<grid, 128, 0, cx.stream>>>(A, base); break;
+            case 5: msm_affine_level_kernel<Fq, 5, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
+            default: msm_affine_level_kernel<Fq, 4, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
+          }
+          B2M_CHECK_LAUNCH();
+          cx.launches += 2;
+          off_in = off_out;
+        }
+        cx.span_end(spl);
+        src_tables = lvl_pts[(LV - 1) & 1].p;
+        src_stride = 0;
+        src_off = off_in;
+        src_sorted = lvl_refs.p;
+        refs = bound[LV];
+      }
+      const uint32_t* src_ends = src_off + 1;   // buckets are contiguous: bucket b ends where b + 1 starts
+      const uint32_t* src_total = src_off + B;
       size_t sp = cx.span_begin("msm_accumulate_kernel", (double)n);
       // References per thread: near MSM_Q, chosen so that the grid is a whole number of waves of
       // (SMs x resident CTAs) -- every thread does the same work, so a partial last wave is pure loss.
-      const size_t refs = (size_t)W * nt;  // upper bound on the reference count (zero digits are rare)
       const size_t wave = (size_t)cx.sm_count * acc_ctas_per_sm * 128;
       size_t waves = (refs + wave * MSM_Q / 2) / (wave * MSM_Q);
       if (waves < 1) waves = 1;
       uint32_t q = (uint32_t)((refs + waves * wave - 1) / (waves * wave));
       if (q < (uint32_t)MSM_Q_MIN) q = MSM_Q_MIN;
       const size_t nthreads = (refs + q - 1) / q;
-      msm_accumulate_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(tables.p, stride, offsets[s].p, cursor[s].p, sorted[s].p,
-                                                                               total[s].p, q, buckets.p + (size_t)j * B, part_pt.p,
+      msm_accumulate_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(src_tables, src_stride, src_off, src_ends, src_sorted,
+                                                                               src_total, q, buckets.p + (size_t)j * B, part_pt.p,
                                                                                part_bkt.p);
       B2M_CHECK_LAUNCH();
       cx.launches++;
       cx.span_end(sp);
       size_t sp1 = cx.span_begin("msm_stitch", (double)n);
       n_long.zero();
-      msm_stitch_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, nthreads, q, offsets[s].p, cursor[s].p,
+      msm_stitch_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, nthreads, q, src_off, src_ends,
                                                                            buckets.p + (size_t)j * B, long_runs.p, n_long.p, long_cap);
       msm_stitch_long_kernel<Fq><<<2 * cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, long_runs.p, n_long.p, long_cap,
                                                                          buckets.p + (size_t)j * B, giant_runs.p, n_long.p + 1);

@@ -14,6 +14,7 @@ template <class F> static void op(int which, const uint32_t* a, const uint32_t* 
     case 4: z = x.inverse(); break;
     case 5: z = x.to_canonical(); break;
     case 6: z = F::from_canonical(x); break;
+    case 7: z = x.inverse_fast(); break;
     default: z = F::zero();
   }
   memcpy(r, z.l, sizeof(z.l));
@@ -48,4 +49,50 @@ template <class Fq> static void cop(int which, const uint32_t* pts, const uint8_
 }
 extern "C" void curve_op(int curve, int which, const uint32_t* pts, const uint8_t* neg, int n, const uint32_t* k, int klimbs, uint32_t* out) {
   if (curve == 0) cop<FqBls>(which, pts, neg, n, k, klimbs, out); else cop<FqBn>(which, pts, neg, n, k, klimbs, out);
+}
+
+#include <vector>
+#include "../../marlin_b200/csrc/msm_affine.cuh"
+// Batched-affine levels on the host, one "thread" after the other: `levels` levels over the bucket-sorted
+// references, then every bucket's remaining points are summed with XYZZ additions (what the XYZZ pass does).
+template <class Fq>
+static void run_levels(const uint32_t* tables, const uint32_t* refs, const uint32_t* off0, uint32_t B, int levels, uint32_t T, uint32_t* out_buckets) {
+  const Affine<Fq>* tab = reinterpret_cast<const Affine<Fq>*>(tables);
+  const uint2* sorted = reinterpret_cast<const uint2*>(refs);
+  std::vector<uint32_t> off_in(off0, off0 + B + 1), off_out(B + 1);
+  std::vector<Affine<Fq>> in, out;
+  std::vector<uint2> out_refs;
+  for (int l = 0; l < levels; l++) {
+    off_out[0] = 0;
+    for (uint32_t b = 0; b < B; b++) off_out[b + 1] = off_out[b] + (off_in[b + 1] - off_in[b] + 1) / 2;
+    const uint32_t total = off_out[B];
+    const uint32_t nthreads = (total + T - 1) / T;
+    out.assign(total, Affine<Fq>::inf());
+    out_refs.assign(total, uint2{0, 0});
+    std::vector<Fq> pref((size_t)T * (nthreads ? nthreads : 1));
+    std::vector<uint4> meta((size_t)T * (nthreads ? nthreads : 1));
+    AffLevel<Fq> A{tab, 0, sorted, in.data(), off_in.data(), off_out.data(), B, out.data(), l == levels - 1 ? out_refs.data() : nullptr,
+                   pref.data(), meta.data(), T, nthreads};
+    for (uint32_t t = 0; t < nthreads; t++) {
+      if (l == 0) aff_plan_thread<Fq, true>(A, t); else aff_plan_thread<Fq, false>(A, t);
+    }
+    for (uint32_t t = 0; t < nthreads; t++) {
+      if (T & 1) aff_level_thread<Fq, true>(A, l == 0 ? tab : in.data(), t); else aff_level_thread<Fq, false>(A, l == 0 ? tab : in.data(), t);
+    }
+    in.swap(out);
+    off_in = off_out;
+  }
+  std::vector<XYZZ<Fq>> acc(B, XYZZ<Fq>::inf());
+  if (levels == 0) {
+    for (uint32_t b = 0; b < B; b++)
+      for (uint32_t i = off0[b]; i < off0[b + 1]; i++) acc[b].add_mixed(tab[sorted[i].x & 0x7fffffffu], sorted[i].x >> 31);
+  } else {
+    for (uint32_t i = 0; i < off_in[B]; i++) acc[out_refs[i].y].add_mixed(in[out_refs[i].x], false);
+  }
+  Affine<Fq>* ob = reinterpret_cast<Affine<Fq>*>(out_buckets);
+  for (uint32_t b = 0; b < B; b++) ob[b] = acc[b].to_affine();
+}
+extern "C" void affine_levels_host(int curve, const uint32_t* tables, const uint32_t* refs, const uint32_t* off0, uint32_t B, int levels, uint32_t T,
+                                   uint32_t* out_buckets) {
+  if (curve == 0) run_levels<FqBls>(tables, refs, off0, B, levels, T, out_buckets); else run_levels<FqBn>(tables, refs, off0, B, levels, T, out_buckets);
 }

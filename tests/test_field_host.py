@@ -48,6 +48,14 @@ def test_montgomery_ops(hostlib, fi, field):
     for _ in range(3):
         a = rnd.randrange(1, p)
         assert call(4, a, 0) * a % p == R * R % p
+    # binary-Euclid inverse (csrc/field.cuh inverse_fast): a^-1 in Montgomery form is a^-1 * R^2 as an integer
+    special = [1, 2, 3, 4, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, R % p, R * R % p, 1 << 32, 1 << 64, (1 << 64) + (1 << 33),
+               1 << (p.bit_length() - 1), (1 << (p.bit_length() - 1)) - 1, p - (1 << 40), 0xffffffff, 0xffffffff00000000]
+    special += [(1 << k) % p for k in range(1, 32 * n, 17)] + [p - ((1 << k) % p) for k in range(1, 32 * n, 29)]
+    for it in range(3000):
+        a = special[it] if it < len(special) else rnd.randrange(1, p)
+        assert call(7, a, 0) == pow(a, -1, p) * R * R % p, hex(a)
+    assert call(7, 0, 0) == 0
 
 
 @pytest.mark.parametrize("ci,curve", list(enumerate([BLS12_381, BN254])), ids=lambda x: getattr(x, "name", x))
@@ -91,3 +99,57 @@ def test_xyzz_group_law(hostlib, ci, curve):
     flat = pack(P)
     hostlib.curve_op(ci, 2, (ctypes.c_uint32 * len(flat))(*flat), (ctypes.c_uint8 * 1)(0), 1, K, 8, out)
     assert unpack(out) == ec.scalar_mul(curve, k, P)
+
+
+@pytest.mark.parametrize("ci,curve", list(enumerate([BLS12_381, BN254])), ids=lambda x: getattr(x, "name", x))
+def test_batched_affine_levels(hostlib, ci, curve):
+    """csrc/msm_affine.cuh on the host: L levels of pairwise affine additions with one shared inversion per
+    thread, then the XYZZ tail, must give every bucket's sum -- including doubled references (P + P),
+    cancelling ones (P - P, whose infinity then meets other points) and odd / empty / single-point buckets."""
+    import numpy as np
+    fq = curve.fq
+    n32 = 12 if ci == 0 else 8
+    rnd = random.Random(11 + ci)
+    n_tab, B = 24, 13
+    tab = [ec.scalar_mul(curve, rnd.randrange(1, curve.fr.p), curve.g) for _ in range(n_tab)]
+
+    def limbs(v):
+        m = fq.to_mont(v)
+        return [(m >> (32 * i)) & 0xffffffff for i in range(n32)]
+
+    tab_l = np.array(sum((limbs(P[0]) + limbs(P[1]) for P in tab), []), dtype=np.uint32)
+    for trial in range(6):
+        buckets = [[] for _ in range(B)]
+        for b in range(B):
+            m = [0, 1, 2, 3, 5, 8, 17, 40][rnd.randrange(8)] if trial else [0, 1, 2, 2, 3, 4, 4, 6, 7, 9, 16, 31, 33][b]
+            for _ in range(m):
+                buckets[b].append((rnd.randrange(n_tab), rnd.randrange(2)))
+            if m >= 4:  # adjacent equal and opposite references: doubling and cancellation at level 0 ...
+                buckets[b][0] = buckets[b][1]
+                buckets[b][2] = (buckets[b][3][0], 1 - buckets[b][3][1])
+            if m >= 8:  # ... and at level 1: (A + B) + (A + B), (A + B) - (A + B)
+                buckets[b][4:8] = [buckets[b][4], buckets[b][5], buckets[b][4], buckets[b][5]]
+            if m >= 17:
+                buckets[b][8:12] = [(1, 0), (2, 1), (1, 1), (2, 0)]
+        refs, off = [], [0]
+        for b, lst in enumerate(buckets):
+            for idx, neg in lst:
+                refs += [idx | (neg << 31), b]
+            off.append(off[-1] + len(lst))
+        want = []
+        for lst in buckets:
+            acc = None
+            for idx, neg in lst:
+                acc = ec.affine_add(curve, acc, ec.affine_neg(curve, tab[idx]) if neg else tab[idx])
+            want.append(acc)
+        refs_a = np.array(refs if refs else [0, 0], dtype=np.uint32)
+        off_a = np.array(off, dtype=np.uint32)
+        for levels, T in ((0, 1), (1, 1), (1, 4), (2, 3), (3, 8), (4, 2), (7, 5), (3, 64)):
+            out = np.zeros(B * 2 * n32, dtype=np.uint32)
+            hostlib.affine_levels_host(ci, tab_l.ctypes.data_as(ctypes.c_void_p), refs_a.ctypes.data_as(ctypes.c_void_p),
+                                       off_a.ctypes.data_as(ctypes.c_void_p), B, levels, T, out.ctypes.data_as(ctypes.c_void_p))
+            for b in range(B):
+                x = sum(int(out[b * 2 * n32 + i]) << (32 * i) for i in range(n32))
+                y = sum(int(out[b * 2 * n32 + n32 + i]) << (32 * i) for i in range(n32))
+                got = None if x == 0 and y == 0 else (fq.from_mont(x), fq.from_mont(y))
+                assert got == want[b], (trial, levels, T, b)

@@ -186,3 +186,41 @@ def test_msm_skewed_scalars(b2m_ctx):
             assert util.srs_msm(srs, curve, 0, sc) == util.trapdoor_msm(curve, curve.g, beta, 0, sc)
     finally:
         _lib.lib().b2m_srs_destroy(srs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("levels,T,variant", [(1, 1, 4), (2, 3, 4), (3, 64, 4), (4, 5, 3), (6, 2, 5)])
+def test_msm_affine_levels_forced(b2m_ctx, monkeypatch, levels, T, variant):
+    """The batched-affine levels (csrc/msm_affine.cuh) are skipped for small MSMs; force them on (any size, odd
+    batch lengths, every kernel variant) over the inputs that hit their special cases: colliding bases (P + P,
+    P - P inside a bucket, at level 0 and above), zero / equal / tiny scalars, buckets of every parity."""
+    monkeypatch.setenv("B2M_MSM_AFFINE_LEVELS", str(levels))
+    monkeypatch.setenv("B2M_MSM_AFFINE_T", str(T))
+    monkeypatch.setenv("B2M_MSM_AFFINE_CTAS", str(variant))
+    monkeypatch.setenv("B2M_MSM_AFFINE_MIN_REFS", "0")
+    curve = BLS12_381
+    r = curve.fr.p
+    rnd = random.Random(31 + levels)
+    P = ec.scalar_mul(curve, 5, curve.g)
+    Q = ec.scalar_mul(curve, 9, curve.g)
+    pts = [P, P, ec.affine_neg(curve, P), Q, P, None, Q, ec.affine_neg(curve, Q)] * 8
+    srs = util.make_srs(b2m_ctx, curve, util.points_to_limbs(curve, pts), window_bits=8)
+    try:
+        for trial in range(4):
+            sc = [rnd.randrange(r) for _ in pts] if trial else [3] * len(pts)
+            assert util.srs_msm(srs, curve, 0, sc) == ec.msm_naive(curve, pts, sc)
+    finally:
+        _lib.lib().b2m_srs_destroy(srs)
+    n = 1 << 12
+    beta = 3  # tiny beta: beta^i * g collide with the 2^(c w) multiples of the window tables
+    powers = util.gpu_powers(b2m_ctx, curve, curve.g, beta, n)
+    for wb in (8, 0):
+        srs = util.make_srs(b2m_ctx, curve, powers, window_bits=wb)
+        try:
+            v, w = rnd.randrange(r), rnd.randrange(r)
+            cases = [[v] * n, [v if i % 3 else w for i in range(n)], [(i % 7) + 1 for i in range(n)], [r - 1 - (i % 2) for i in range(n)],
+                     [rnd.randrange(r) for _ in range(n)], [0] * n, [1] * 5, [rnd.randrange(r) for _ in range(777)]]
+            for sc in cases:
+                assert util.srs_msm(srs, curve, 1, sc[:n - 1]) == util.trapdoor_msm(curve, curve.g, beta, 1, sc[:n - 1])
+        finally:
+            _lib.lib().b2m_srs_destroy(srs)
