@@ -29,7 +29,7 @@ constexpr uint32_t MSM_BKT_MASK = (1u << MSM_BKT_BITS) - 1;
 constexpr uint32_t MSM_NO_DIGIT = 0xffffffffu;
 constexpr int MSM_MAX_BATCH = 8;   // MSMs per run_batch call
 constexpr int MSM_MAX_AFFINE_LEVELS = 6;
-constexpr size_t MSM_AFFINE_MIN_REFS = (size_t)1 << 19;  // smaller MSMs skip the batched-affine levels (launch-latency bound)
+constexpr size_t MSM_AFFINE_MIN_REFS = (size_t)1 << 23;  // MSMs with fewer bucket references skip the batched-affine levels (measured: a loss below ~2^22)
 
 template <class Fr, class Fq>
 struct MsmJob {
@@ -56,7 +56,10 @@ struct Msm {
   size_t n_extra = 0;  // further fixed bases (powers_of_gamma_g) appended after them
   size_t stride = 0;   // n_srs + n_extra: entries per window table
   int c = 0, W = 0;
-  int affine_levels = 3;    // batched-affine levels run before the XYZZ bucket pass (msm_affine.cuh); B2M_MSM_AFFINE_LEVELS
+  // batched-affine levels run before the XYZZ bucket pass (msm_affine.cuh); override: B2M_MSM_AFFINE_LEVELS.
+  // Off for a 254-bit Fq: its multiplications are so cheap that the levels' extra memory traffic costs more
+  // than the saved multiplications (BN254 2^20: 126.6 ms with, 120.6 ms without).
+  int affine_levels = Fq::N > 8 ? 3 : 0;
   int affine_ctas = 4;      // level-kernel variant: resident CTAs per SM it is compiled for (B2M_MSM_AFFINE_CTAS: 3 = with prefetch, 4, 5)
   size_t affine_min_refs = MSM_AFFINE_MIN_REFS;  // B2M_MSM_AFFINE_MIN_REFS
   int affine_T = 64;        // additions per thread and inversion in those levels; B2M_MSM_AFFINE_T
