@@ -224,25 +224,36 @@ def main():
     value = n / (ms_step / 1e3)
     e2e_value = n * args.steps / wall_e2e
     peaks, peak_kind = measured_peaks()
-    acc = kern.get("msm_accumulate_kernel", {"ms": 0.0, "units": 0.0, "launches": 0})
+    zero = {"ms": 0.0, "units": 0.0, "launches": 0}
+    acc = kern.get("msm_accumulate_kernel", zero)
+    lev = kern.get("msm_affine_levels", zero)
     pair_bytes = 128 if args.curve == "bls12_381" else 96
-    achieved = (acc["units"] * pair_bytes / (acc["ms"] / 1e3) / 1e9) if acc["ms"] else None
+    # The dominant kernels are the MSM bucket pass: (3 batched-affine level kernels, where the MSM is large enough)
+    # + the XYZZ accumulate kernel on what is left.  One "launch" below = the bucket pass of one MSM.
+    bucket_ms = acc["ms"] + lev["ms"]
+    achieved = (acc["units"] * pair_bytes / (bucket_ms / 1e3) / 1e9) if bucket_ms else None
     from marlin_b200 import _lib as _plib
     win_bits = int(_plib.lib().b2m_srs_window_bits(srs.handle))
+    aff_levels = int(_plib.lib().b2m_srs_affine_levels(srs.handle))
     scalar_bits = 255 if args.curve == "bls12_381" else 254
-    msm_windows, alu_peak = (scalar_bits + win_bits) // win_bits, None  # signed c-bit windows per scalar (c = 20 -> 13)
+    msm_windows, mul_peak = (scalar_bits + win_bits) // win_bits, None  # signed c-bit windows per scalar (c = 20 -> 13)
     try:
         with open(os.path.join(ROOT, "profiles", "r01_microbench_int_alu.json")) as f:
             mb = json.load(f)
-        alu_peak = max(v for k, v in mb.items() if k.startswith("g1_madd")) if args.curve == "bls12_381" else None
+        mul_peak = max(v for k, v in mb.items() if k.startswith("fq_mul")) if args.curve == "bls12_381" else None
     except Exception:
         pass
-    traffic = None  # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/), scaled to this run's mean launch
+    # field multiplications the bucket pass performs: an affine addition with a shared inversion is 6, an XYZZ mixed
+    # addition 10; L levels leave 1/2^L of the references to the XYZZ kernel
+    share = 0.5 ** aff_levels
+    muls = msm_windows * (lev["units"] * ((1 - share) * 6 + share * 10) + (acc["units"] - lev["units"]) * 10)
+    traffic = None  # DRAM bytes per launch from the committed `ncu --set full` captures (profiles/), scaled to this run's mean launch
     try:
         with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
             tr = json.load(f)
         if args.curve == "bls12_381" and acc["launches"]:
-            traffic = tr["dram_bytes_per_pair"] * acc["units"] / acc["launches"]
+            per_pair = tr["levels"]["dram_bytes_per_pair"] if lev["launches"] else tr["dram_bytes_per_pair"]
+            traffic = per_pair * acc["units"] / acc["launches"]
     except Exception:
         pass
     line = {
@@ -259,18 +270,22 @@ def main():
         "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": int(circ.instance.nbytes + circ.witness.nbytes),
                 "d2h_bytes_per_step": len(proof) + 15 * 96, "host_memory": "pinned"},
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "kernel": "msm_accumulate_kernel", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": ("MSM bucket pass: msm_affine_level_kernel x%d + msm_accumulate_kernel" % aff_levels) if lev["launches"]
+                     else "msm_accumulate_kernel", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                      "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_source": peak_kind,
                      "algorithmic_bytes_per_launch": (acc["units"] * pair_bytes / acc["launches"]) if acc["launches"] else None,
-                     "algorithmic_bytes_per_pair": pair_bytes,
-                     "note": "integer-ALU bound (profiles/r01_microbench_int_alu.json); see DESIGN.md Rooflines"},
-        # the meaningful roofline of this kernel: XYZZ mixed additions per second against the whole-chip
+                     "algorithmic_bytes_per_pair": pair_bytes, "launch": "the bucket pass of one MSM (mean over the proof's MSMs)",
+                     "note": "bound by the 32-bit integer multiplier, not by HBM (roofline_int_alu; DESIGN.md Rooflines); traffic = "
+                             "level kernels only (profiles/r01_ncu_affine_levels.md)"},
+        # the meaningful roofline of these kernels: Fq multiplications per second against the whole-chip
         # integer-multiply microbenchmark (profiles/r01_microbench_int_alu.json, tools/microbench.cu)
-        "roofline_int_alu": {"kernel": "msm_accumulate_kernel", "unit": "G mixed additions/s",
-                             "achieved": (acc["units"] * msm_windows / (acc["ms"] / 1e3) / 1e9) if acc["ms"] else None,
-                             "peak": alu_peak, "frac": (acc["units"] * msm_windows / (acc["ms"] / 1e3) / 1e9 / alu_peak) if acc["ms"] and alu_peak else None,
-                             "peak_source": "tools/microbench.cu g1_madd (measured on this pool's B200)"},
-        "msm_accumulate_ms_per_step": acc["ms"] / args.steps if acc["ms"] else None,
+        "roofline_int_alu": {"kernel": "MSM bucket pass", "unit": "G Fq multiplications/s",
+                             "achieved": (muls / (bucket_ms / 1e3) / 1e9) if bucket_ms else None,
+                             "peak": mul_peak, "frac": (muls / (bucket_ms / 1e3) / 1e9 / mul_peak) if bucket_ms and mul_peak else None,
+                             "affine_levels": aff_levels, "muls_per_affine_add": 6, "muls_per_xyzz_add": 10,
+                             "bucket_additions_per_s_G": (acc["units"] * msm_windows / (bucket_ms / 1e3) / 1e9) if bucket_ms else None,
+                             "peak_source": "tools/microbench.cu fq_mul (measured on this pool's B200)"},
+        "msm_bucket_pass_ms_per_step": bucket_ms / args.steps if bucket_ms else None,
         "kernels": kern, "phases_ms": phases, "dev_ms_steps": dev_ms, "setup_s": setup_s, "proof_bytes": len(proof), "proof_sha256": proof_sha,
     }
     if rank == 0:

@@ -102,6 +102,9 @@ int b2m_srs_create(b2m_ctx* ctx, int curve, const uint64_t* powers_of_g, size_t 
 void b2m_srs_destroy(b2m_srs* srs);
 size_t b2m_srs_size(const b2m_srs* srs);
 int b2m_srs_window_bits(const b2m_srs* srs);
+/* Batched-affine levels the MSMs of this key run before the XYZZ bucket pass (0: none; MSMs with few bucket
+ * references skip them regardless).  Diagnostic, like b2m_srs_window_bits. */
+int b2m_srs_affine_levels(const b2m_srs* srs);
 /* MSM over the slice powers_of_g[base_off .. base_off+n) with canonical host scalars. */
 int b2m_srs_msm(b2m_srs* srs, size_t base_off, const uint64_t* scalars, size_t n, uint64_t* out_xy,
                 int* out_is_inf);

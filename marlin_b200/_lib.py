@@ -65,6 +65,7 @@ def lib():
         L.b2m_srs_size.argtypes = [vp]
         L.b2m_srs_size.restype = sz
         L.b2m_srs_window_bits.argtypes = [vp]
+        L.b2m_srs_affine_levels.argtypes = [vp]
         L.b2m_srs_msm.argtypes = [vp, sz, vp, sz, vp, P(ci)]
         L.b2m_g1_powers.argtypes = [vp, ci, vp, vp, sz, vp]
         L.b2m_pc_commit.argtypes = [vp, ci, sz, vp, vp, vp, vp, P(Rng), vp, vp, vp, vp, sz]

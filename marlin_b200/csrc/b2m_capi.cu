@@ -104,6 +104,7 @@ void b2m_srs_destroy(b2m_srs* srs) {
 
 size_t b2m_srs_size(const b2m_srs* srs) { return srs ? srs->n_g : 0; }
 int b2m_srs_window_bits(const b2m_srs* srs) { return srs ? srs->window_bits() : 0; }
+int b2m_srs_affine_levels(const b2m_srs* srs) { return srs ? srs->affine_levels() : 0; }
 
 int b2m_srs_msm(b2m_srs* srs, size_t base_off, const uint64_t* scalars, size_t n, uint64_t* out_xy, int* out_is_inf) {
   return guard([&] {

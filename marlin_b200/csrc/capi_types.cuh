@@ -72,5 +72,7 @@ struct b2m_srs {
     c->cx.sync();
   }
   int window_bits() const { return bls ? bls->c : bn->c; }
+  int affine_levels() const { return bls ? bls->affine_levels : bn->affine_levels; }
+  size_t affine_min_refs() const { return bls ? bls->affine_min_refs : bn->affine_min_refs; }
 };
 
