@@ -378,11 +378,11 @@ class G2Key:
 
     def __init__(self, pp, bounds=()):
         from . import pairing
-        self.pairing = pairing
-        self.h = pairing.g2_generator()
-        self.beta_h = pairing.e12_mul(pp.beta, self.h)
+        self.pairing = pg = pairing.for_curve(pp.curve)  # BLS12-381 or BN254
+        self.h = pg.g2_generator()
+        self.beta_h = pg.e12_mul(pp.beta, self.h)
         p = pp.curve.fr.p
-        self.neg_powers = {d: pairing.e12_mul(pow(pow(pp.beta, pp.max_degree - d, p), -1, p), self.h) for d in bounds}
+        self.neg_powers = {d: pg.e12_mul(pow(pow(pp.beta, pp.max_degree - d, p), -1, p), self.h) for d in bounds}
 
     def check(self, curve, plain, by_bound, w, z):
         pg = self.pairing

@@ -131,7 +131,7 @@ def prove(pk, circuit, zk_rng, engine=None):
 
 def verify(pk, public_input, proof, g2=None):
     """[R src/lib.rs:315-433].  g2 = None: `PC::check_combinations` through the SRS trapdoor (kzg.py);
-    g2 = kzg.G2Key: through the pairing product the reference computes (BLS12-381 only)."""
+    g2 = kzg.G2Key: through the pairing product the reference computes (oracle/pairing.py: BLS12-381, BN254)."""
     curve, scheme, ck = pk.curve, pk.scheme, pk.ck
     f = curve.fr
     p = f.p

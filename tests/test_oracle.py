@@ -226,21 +226,24 @@ def test_cpp_prover_reproduces_golden(case):
         cp.close()
 
 
-def test_pairing_bilinear_and_nondegenerate():
-    from oracle import pairing as pg
-    c = BLS12_381
+@pytest.mark.parametrize("c", [BLS12_381, BN254], ids=lambda c: c.name)
+def test_pairing_bilinear_and_nondegenerate(c):
+    from oracle import pairing
+    pg = pairing.for_curve(c)
     Q = pg.g2_generator()
+    assert pg.e12_on_curve(Q) and pg.e12_mul(pg.R, Q) is None
     e1 = pg.pairing(c.g, Q)
     assert e1 != pg.Fq12.one() and e1.pow(pg.R) == pg.Fq12.one()
     a, b = 0x1234567, 0x7654321
     assert pg.pairing(ec.scalar_mul(c, a, c.g), pg.e12_mul(b, Q)) == e1.pow(a * b % pg.R)
     assert pg.pairing_product_is_one([(ec.scalar_mul(c, a, c.g), Q), (ec.affine_neg(c, c.g), pg.e12_mul(a, Q))])
+    assert not pg.pairing_product_is_one([(ec.scalar_mul(c, a, c.g), Q), (ec.affine_neg(c, c.g), pg.e12_mul(a + 1, Q))])
 
 
+@pytest.mark.parametrize("curve", [BLS12_381, BN254], ids=lambda c: c.name)
 @pytest.mark.parametrize("scheme", [kzg.MARLIN, kzg.SONIC])
-def test_verify_with_real_pairings(scheme):
+def test_verify_with_real_pairings(scheme, curve):
     """The reference's own acceptance test [src/test.rs:158-161] with `KZG10::check` done by pairings, no trapdoor."""
-    curve = BLS12_381
     f = curve.fr
     rng = R.test_rng()
     a, b = R.field_rand(f, rng), R.field_rand(f, rng)
