@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--cpu-log-n", type=int, default=16, help="instance size of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--window-bits", type=int, default=0, help="MSM window override (0: chosen from the per-rank MSM size)")
+    ap.add_argument("--save-proof", default=None, help="write the hashed proof, the verifier key and the public data to this JSON file "
+                                                       "(checked afterwards on a CPU by tests/verify_saved_proof.py)")
     return ap.parse_args()
 
 
@@ -214,7 +216,14 @@ def main():
     # outside every timed region: a proof from a fresh zk stream, hashed, so that runs with different window sizes,
     # GPU counts or library builds can be compared byte for byte
     import hashlib
-    proof_sha = hashlib.sha256(m.prove(pk, circ, api.ZkRng())).hexdigest()
+    proof_chk = m.prove(pk, circ, api.ZkRng())
+    proof_sha = hashlib.sha256(proof_chk).hexdigest()
+    if args.save_proof and rank == 0:
+        from marlin_b200 import fields
+        with open(args.save_proof, "w") as f:
+            json.dump({"curve": args.curve, "pc": args.pc, "log_n": args.log_n, "n_gpus": world, "max_degree": int(srs.max_degree),
+                       "beta": 0x5eed5eed5eed5eed5eed5eed, "gamma": 7, "public_input": [str(a * b % fields.FR_MODULUS[cid])],
+                       "proof_hex": proof_chk.hex(), "vk_hex": bytes(pk.vk_bytes).hex(), "proof_sha256": proof_sha}, f)
 
     ms_step = sum(dev_ms) / len(dev_ms)
     if dist is not None:  # max over ranks

@@ -257,3 +257,35 @@ def test_verify_with_real_pairings(scheme, curve):
     g2 = kzg.G2Key(srs, pk.ck.enforced_degree_bounds)
     assert marlin.verify(pk, [c, d], proof, g2)
     assert not marlin.verify(pk, [a, a], proof, g2)
+
+
+@pytest.mark.parametrize("curve", [BLS12_381, BN254], ids=lambda c: c.name)
+def test_saved_proof_checker(tmp_path, curve):
+    """tests/verify_saved_proof.py (the CPU-side check of `bench.py --save-proof` files) on an oracle-made file:
+    accepted as written, rejected after one flipped proof byte."""
+    import json
+    import verify_saved_proof as vsp
+    f = curve.fr
+    n = 32
+    a, b = 0x1234567890abcdef1234567890abcdef % f.p, 0xfedcba0987654321fedcba0987654321 % f.p
+    beta, gamma = 0x5eed5eed5eed5eed5eed5eed, 7
+    circ = r1cs.dummy_circuit(f, a, b, 10, n)
+    srs = marlin.universal_setup(curve, n, n, 3 * n, beta=beta, g_scalar=1, gamma=gamma)
+    eng = kzg.Engine(use_trapdoor=True)
+    pk = marlin.index(srs, circ, kzg.MARLIN, eng)
+    proof = marlin.serialize_proof(curve, kzg.MARLIN, marlin.prove(pk, circ, R.test_rng(), eng))
+    rec = {"curve": curve.name, "pc": "marlin_kzg10", "log_n": 5, "n_gpus": 0, "max_degree": srs.max_degree, "beta": beta, "gamma": gamma,
+           "public_input": [str(a * b % f.p)], "proof_hex": proof.hex(), "vk_hex": pk.vk_bytes.hex()}
+    path = tmp_path / "proof.json"
+    path.write_text(json.dumps(rec))
+    res = vsp.verify_file(str(path))
+    assert res["ok"] and res["pairing"] and res["num_constraints"] == n
+    bad = bytearray(proof)
+    bad[-40] ^= 1  # inside the last evaluation / opening data
+    rec["proof_hex"] = bytes(bad).hex()
+    path.write_text(json.dumps(rec))
+    try:
+        ok = vsp.verify_file(str(path))["ok"]
+    except (ValueError, AssertionError):
+        ok = False  # the flipped byte can also make a compressed point undecodable
+    assert not ok
