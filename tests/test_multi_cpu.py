@@ -47,9 +47,8 @@ def _worker(rank, world, port, n, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [1, 7, 32])
-def test_sharded_msm_world2(n):
-    world = 2
+@pytest.mark.parametrize("n,world", [(1, 2), (7, 2), (32, 2), (10, 3)])
+def test_sharded_msm_world2(n, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + random.randrange(2000)
