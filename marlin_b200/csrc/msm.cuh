@@ -60,6 +60,7 @@ struct Msm {
   // Off for a 254-bit Fq: its multiplications are so cheap that the levels' extra memory traffic costs more
   // than the saved multiplications (BN254 2^20: 126.6 ms with, 120.6 ms without).
   int affine_levels = Fq::N > 8 ? 3 : 0;
+  int affine_ctas_upper = 4;  // the same for levels >= 1 (streaming operands); B2M_MSM_AFFINE_CTAS_UPPER, 6 = two-chain ILP variant
   int affine_ctas = 4;      // level-kernel variant: resident CTAs per SM it is compiled for (B2M_MSM_AFFINE_CTAS: 3 = with prefetch, 4, 5)
   size_t affine_min_refs = MSM_AFFINE_MIN_REFS;  // B2M_MSM_AFFINE_MIN_REFS
   int affine_T = 64;        // additions per thread and inversion in those levels; B2M_MSM_AFFINE_T

@@ -283,4 +283,116 @@ B2M_HD void aff_level_thread(const AffLevel<Fq>& A, const Affine<Fq>* base, uint
   }
 }
 
+// ---- ILP variant (opt-in, B2M_MSM_AFFINE_CTAS / _UPPER = 6; not the default: unmeasured at the end of round 1) ------
+// The default thread function above runs ONE dependent multiplication chain in the denominator pass and a chain of
+// four in the addition pass, so a warp rarely has two multiplications in flight.  This variant
+// keeps TWO interleaved prefix chains (even and odd outputs) and handles two outputs per loop iteration, so every
+// multiplication has an independent twin -- the regime in which the XYZZ kernel reaches 90 % of the multiplier peak
+// with 8 warps per SM.  pref[k] holds the product of the denominators of outputs k, k - 2, k - 4, ... (own chain).
+template <class Fq>
+B2M_HD Fq aff_den_or_one(const Affine<Fq>* base, const uint4& m, const Fq& x1, const Fq& x2) {
+  if (!m.w) return Fq::one();
+  if (x1.is_zero() || x2.is_zero() || x1 == x2) {  // rare: infinity, doubling or cancellation
+    Fq den;
+    const AffKind kind = aff_classify(aff_signed(aff_ld(base, m.x), m.x), aff_signed(aff_ld(base, m.y), m.y), &den);
+    return (kind == AFF_ADD || kind == AFF_DBL) ? den : Fq::one();
+  }
+  return x2 - x1;
+}
+// one output given the inverse of its denominator; returns the denominator (one() if the output needs none)
+template <class Fq>
+B2M_HD Affine<Fq> aff_finish(const Affine<Fq>& P, const Affine<Fq>& Q, bool pair, const Fq& dinv, Fq* den_out) {
+  *den_out = Fq::one();
+  if (!pair) return P;
+  Fq den;
+  const AffKind kind = aff_classify(P, Q, &den);
+  if (kind == AFF_COPY_P) return P;
+  if (kind == AFF_COPY_Q) return Q;
+  if (kind == AFF_INF) return Affine<Fq>::inf();
+  *den_out = den;
+  Fq lam;
+  Affine<Fq> R;
+  if (kind == AFF_ADD) {
+    lam = (Q.y - P.y) * dinv;
+    R.x = lam.sqr() - P.x - Q.x;
+  } else {
+    const Fq xx = P.x.sqr();
+    lam = (xx.dbl() + xx) * dinv;
+    R.x = lam.sqr() - P.x.dbl();
+  }
+  R.y = lam * (P.x - R.x) - P.y;
+  return R;
+}
+template <class Fq>
+B2M_HD void aff_store_out(const AffLevel<Fq>& A, uint32_t o, const Affine<Fq>& R, uint32_t bucket) {
+  B2M_AFF_ST(&A.out[o].x, R.x);
+  B2M_AFF_ST(&A.out[o].y, R.y);
+  if (A.out_refs) {
+    uint2 r;
+    r.x = o;
+    r.y = bucket;
+    A.out_refs[o] = r;
+  }
+}
+
+template <class Fq>
+B2M_HD void aff_level_thread_ilp(const AffLevel<Fq>& A, const Affine<Fq>* base, uint32_t t) {
+  const uint32_t total = B2M_AFF_LDG32(A.off_out + A.B);
+  const uint64_t o0_64 = (uint64_t)t * A.T;
+  if (o0_64 >= total) return;
+  const uint32_t o0 = (uint32_t)o0_64;
+  const uint32_t cnt = total - o0 < A.T ? total - o0 : A.T;
+  const size_t nth = A.nthreads;
+  const uint4* meta = A.meta + t;
+  Fq* pref = A.pref + t;
+  // ---- pass 1: two prefix chains -------------------------------------------------------------------
+  Fq run0 = Fq::one(), run1 = Fq::one();  // chains of the even / odd outputs
+  for (uint32_t k = 0; k < cnt; k += 2) {
+    const bool two = k + 1 < cnt;
+    const uint4 m0 = meta[(size_t)k * nth];
+    const uint4 m1 = two ? meta[(size_t)(k + 1) * nth] : m0;
+    const Fq a1 = aff_ldx(base, m0.x), a2 = aff_ldx(base, m0.y);
+    const Fq b1 = aff_ldx(base, m1.x), b2 = aff_ldx(base, m1.y);
+    const Fq d0 = aff_den_or_one(base, m0, a1, a2);
+    const Fq d1 = two ? aff_den_or_one(base, m1, b1, b2) : Fq::one();
+    run0 = run0 * d0;
+    run1 = run1 * d1;
+    B2M_AFF_ST(pref + (size_t)k * nth, run0);
+    if (two) B2M_AFF_ST(pref + (size_t)(k + 1) * nth, run1);
+  }
+  // ---- one inversion for both chains -------------------------------------------------------------------
+  const Fq inv_all = (run0 * run1).inverse_fast();
+  Fq inv0 = inv_all * run1, inv1 = inv_all * run0;
+  // ---- pass 2: walk back two outputs (one of each chain) at a time ------------------------------------------
+  uint32_t k = cnt;
+  if (cnt & 1u) {  // the top output has no twin: it is the last one of the even chain
+    k--;
+    const uint4 m = meta[(size_t)k * nth];
+    const Affine<Fq> P = aff_signed(aff_ld(base, m.x), m.x), Q = aff_signed(aff_ld(base, m.y), m.y);
+    Fq dinv = inv0;
+    if (k >= 2) dinv = inv0 * B2M_AFF_LD(pref + (size_t)(k - 2) * nth);
+    Fq den;
+    const Affine<Fq> R = aff_finish(P, Q, m.w != 0, dinv, &den);
+    inv0 = inv0 * den;
+    aff_store_out(A, o0 + k, R, m.z);
+  }
+  while (k >= 2) {
+    k -= 2;  // outputs k + 1 (odd chain) and k (even chain)
+    const uint4 m1 = meta[(size_t)(k + 1) * nth];
+    const uint4 m0 = meta[(size_t)k * nth];
+    const Affine<Fq> P1 = aff_signed(aff_ld(base, m1.x), m1.x), Q1 = aff_signed(aff_ld(base, m1.y), m1.y);
+    const Affine<Fq> P0 = aff_signed(aff_ld(base, m0.x), m0.x), Q0 = aff_signed(aff_ld(base, m0.y), m0.y);
+    Fq dinv1 = inv1, dinv0 = inv0;
+    if (k + 1 >= 2) dinv1 = inv1 * B2M_AFF_LD(pref + (size_t)(k - 1) * nth);
+    if (k >= 2) dinv0 = inv0 * B2M_AFF_LD(pref + (size_t)(k - 2) * nth);
+    Fq den1, den0;
+    const Affine<Fq> R1 = aff_finish(P1, Q1, m1.w != 0, dinv1, &den1);
+    const Affine<Fq> R0 = aff_finish(P0, Q0, m0.w != 0, dinv0, &den0);
+    inv1 = inv1 * den1;
+    inv0 = inv0 * den0;
+    aff_store_out(A, o0 + k + 1, R1, m1.z);
+    aff_store_out(A, o0 + k, R0, m0.z);
+  }
+}
+
 }  // namespace b2m

@@ -204,6 +204,13 @@ __global__ void __launch_bounds__(128, MINB) msm_affine_level_kernel(const AffLe
   if (t < A.nthreads) aff_level_thread<Fq, PF>(A, base, t);
 }
 
+// opt-in two-chain variant (msm_affine.cuh aff_level_thread_ilp): B2M_MSM_AFFINE_CTAS / B2M_MSM_AFFINE_CTAS_UPPER = 6
+template <class Fq>
+__global__ void __launch_bounds__(128, 2) msm_affine_level_ilp_kernel(const AffLevel<Fq> A, const Affine<Fq>* __restrict__ base) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < A.nthreads) aff_level_thread_ilp<Fq>(A, base, t);
+}
+
 // Partials are ordered by bucket (they follow the sorted references).  The first partial of each bucket
 // sums the ones that follow it and stores the bucket; a bucket cut into many partials (skewed scalar
 // distributions, e.g. a polynomial whose coefficients are nearly all equal) is queued for
@@ -465,6 +472,8 @@ Msm<Fr, Fq>::Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, const Affine<
   if (const char* e = getenv("B2M_MSM_AFFINE_LEVELS")) affine_levels = atoi(e);
   if (const char* e = getenv("B2M_MSM_AFFINE_T")) affine_T = atoi(e);
   if (const char* e = getenv("B2M_MSM_AFFINE_CTAS")) affine_ctas = atoi(e);
+  affine_ctas_upper = affine_ctas;
+  if (const char* e = getenv("B2M_MSM_AFFINE_CTAS_UPPER")) affine_ctas_upper = atoi(e);
   if (const char* e = getenv("B2M_MSM_AFFINE_MIN_REFS")) affine_min_refs = (size_t)atoll(e);
   if (affine_levels < 0) affine_levels = 0;
   if (affine_levels > MSM_MAX_AFFINE_LEVELS) affine_levels = MSM_MAX_AFFINE_LEVELS;
@@ -643,8 +652,9 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
             msm_affine_plan_kernel<Fq, false><<<div_up(nthreads, 256), 256, 0, cx.stream>>>(A);
           const Affine<Fq>* base = l == 0 ? tables.p : lvl_pts[(l - 1) & 1].p;
           const unsigned grid = div_up(nthreads, 128);
-          switch (affine_ctas) {  // resident CTAs per SM the kernel is compiled for; 3 = with operand prefetch
-            case 3: msm_affine_level_kernel<Fq, 3, true><<<grid, 128, 0, cx.stream>>>(A, base); break;
+          switch (l == 0 ? affine_ctas : affine_ctas_upper) {  // kernel variant: resident CTAs per SM it is compiled for
+            case 6: msm_affine_level_ilp_kernel<Fq><<<grid, 128, 0, cx.stream>>>(A, base); break;  // two chains, 2 CTAs/SM
+            case 3:  // with operand prefetch msm_affine_level_kernel<Fq, 3, true><<<grid, 128, 0, cx.stream>>>(A, base); break;
             case 5: msm_affine_level_kernel<Fq, 5, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
             default: msm_affine_level_kernel<Fq, 4, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
           }

@@ -56,7 +56,8 @@ extern "C" void curve_op(int curve, int which, const uint32_t* pts, const uint8_
 // Batched-affine levels on the host, one "thread" after the other: `levels` levels over the bucket-sorted
 // references, then every bucket's remaining points are summed with XYZZ additions (what the XYZZ pass does).
 template <class Fq>
-static void run_levels(const uint32_t* tables, const uint32_t* refs, const uint32_t* off0, uint32_t B, int levels, uint32_t T, uint32_t* out_buckets) {
+static void run_levels(const uint32_t* tables, const uint32_t* refs, const uint32_t* off0, uint32_t B, int levels, uint32_t T, uint32_t* out_buckets,
+                       int variant) {
   const Affine<Fq>* tab = reinterpret_cast<const Affine<Fq>*>(tables);
   const uint2* sorted = reinterpret_cast<const uint2*>(refs);
   std::vector<uint32_t> off_in(off0, off0 + B + 1), off_out(B + 1);
@@ -77,7 +78,10 @@ static void run_levels(const uint32_t* tables, const uint32_t* refs, const uint3
       if (l == 0) aff_plan_thread<Fq, true>(A, t); else aff_plan_thread<Fq, false>(A, t);
     }
     for (uint32_t t = 0; t < nthreads; t++) {
-      if (T & 1) aff_level_thread<Fq, true>(A, l == 0 ? tab : in.data(), t); else aff_level_thread<Fq, false>(A, l == 0 ? tab : in.data(), t);
+      const Affine<Fq>* base = l == 0 ? tab : in.data();
+      if (variant == 1) aff_level_thread_ilp<Fq>(A, base, t);
+      else if (T & 1) aff_level_thread<Fq, true>(A, base, t);
+      else aff_level_thread<Fq, false>(A, base, t);
     }
     in.swap(out);
     off_in = off_out;
@@ -93,6 +97,7 @@ static void run_levels(const uint32_t* tables, const uint32_t* refs, const uint3
   for (uint32_t b = 0; b < B; b++) ob[b] = acc[b].to_affine();
 }
 extern "C" void affine_levels_host(int curve, const uint32_t* tables, const uint32_t* refs, const uint32_t* off0, uint32_t B, int levels, uint32_t T,
-                                   uint32_t* out_buckets) {
-  if (curve == 0) run_levels<FqBls>(tables, refs, off0, B, levels, T, out_buckets); else run_levels<FqBn>(tables, refs, off0, B, levels, T, out_buckets);
+                                   uint32_t* out_buckets, int variant) {
+  if (curve == 0) run_levels<FqBls>(tables, refs, off0, B, levels, T, out_buckets, variant);
+  else run_levels<FqBn>(tables, refs, off0, B, levels, T, out_buckets, variant);
 }

@@ -144,12 +144,14 @@ def test_batched_affine_levels(hostlib, ci, curve):
             want.append(acc)
         refs_a = np.array(refs if refs else [0, 0], dtype=np.uint32)
         off_a = np.array(off, dtype=np.uint32)
-        for levels, T in ((0, 1), (1, 1), (1, 4), (2, 3), (3, 8), (4, 2), (7, 5), (3, 64)):
+        # variant 0: default thread function (odd T: with operand prefetch), variant 1: the two-chain ILP one
+        for levels, T, variant in ((0, 1, 0), (1, 1, 0), (1, 4, 0), (2, 3, 0), (3, 8, 0), (4, 2, 0), (7, 5, 0), (3, 64, 0),
+                                   (1, 1, 1), (1, 2, 1), (2, 3, 1), (3, 8, 1), (4, 5, 1), (7, 4, 1), (3, 64, 1), (2, 7, 1)):
             out = np.zeros(B * 2 * n32, dtype=np.uint32)
             hostlib.affine_levels_host(ci, tab_l.ctypes.data_as(ctypes.c_void_p), refs_a.ctypes.data_as(ctypes.c_void_p),
-                                       off_a.ctypes.data_as(ctypes.c_void_p), B, levels, T, out.ctypes.data_as(ctypes.c_void_p))
+                                       off_a.ctypes.data_as(ctypes.c_void_p), B, levels, T, out.ctypes.data_as(ctypes.c_void_p), variant)
             for b in range(B):
                 x = sum(int(out[b * 2 * n32 + i]) << (32 * i) for i in range(n32))
                 y = sum(int(out[b * 2 * n32 + n32 + i]) << (32 * i) for i in range(n32))
                 got = None if x == 0 and y == 0 else (fq.from_mont(x), fq.from_mont(y))
-                assert got == want[b], (trial, levels, T, b)
+                assert got == want[b], (trial, levels, T, variant, b)
