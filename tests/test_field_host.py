@@ -118,7 +118,7 @@ def test_batched_affine_levels(hostlib, ci, curve):
         return [(m >> (32 * i)) & 0xffffffff for i in range(n32)]
 
     tab_l = np.array(sum((limbs(P[0]) + limbs(P[1]) for P in tab), []), dtype=np.uint32)
-    for trial in range(6):
+    for trial in range(4):
         buckets = [[] for _ in range(B)]
         for b in range(B):
             m = [0, 1, 2, 3, 5, 8, 17, 40][rnd.randrange(8)] if trial else [0, 1, 2, 2, 3, 4, 4, 6, 7, 9, 16, 31, 33][b]
