@@ -11,8 +11,9 @@ timed region exactly as in benches/bench.rs:79-101.
   roofline     : the dominant kernel (msm_accumulate_kernel) -- algorithmic bytes (128 B per
                  (base, scalar) pair) / CUDA-event kernel time / measured HBM peak
   cpu_baseline : the oracle's C++ restatement of the reference prover (oracle/cport/prover.cpp) timed on this
-                 box's host cores (rank 0, N = 1) on a bounded sample: one full prove of a 2^16-constraint
-                 instance of the same circuit family
+                 box's host cores (rank 0, N = 1) on a bounded sample: full proves of a 2^16-constraint
+                 instance of the same circuit family (~10-30 s of CPU work)
+  --impl reference : the same CPU prover on the SAME 2^log_n configuration as the GPU arm (see run_reference)
 
 N > 1 (torchrun, one rank per GPU): every rank runs the prover, each MSM is sharded by base/scalar
 chunk and the partial sums are exchanged with one NCCL all-gather per MSM (DESIGN.md "Multi-GPU");
@@ -39,9 +40,13 @@ def parse_args():
     ap.add_argument("--log-n", type=int, default=20, help="log2 of the number of constraints (BASELINE config 2: 20)")
     ap.add_argument("--pc", default="marlin_kzg10", choices=["marlin_kzg10", "sonic_kzg10"])
     ap.add_argument("--curve", default="bls12_381", choices=["bls12_381", "bn254"])
-    ap.add_argument("--cpu-log-n", type=int, default=16, help="instance size of the bounded CPU baseline sample")
+    ap.add_argument("--cpu-log-n", type=int, default=16, help="instance size of the bounded cpu_baseline sample of the GPU arm's line")
+    ap.add_argument("--ref-log-n", type=int, default=0, help="--impl reference: instance size (0 = the same 2^log_n as the GPU arm)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="--impl reference: stop starting new proves once set-up + proves "
+                                                                       "would exceed this wall time (at least one prove always runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--window-bits", type=int, default=0, help="MSM window override (0: chosen from the per-rank MSM size)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the post-run proof check (oracle verifier with the real pairing)")
     ap.add_argument("--save-proof", default=None, help="write the hashed proof, the verifier key and the public data to this JSON file "
                                                        "(checked afterwards on a CPU by tests/verify_saved_proof.py)")
     return ap.parse_args()
@@ -113,29 +118,40 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(args, repeats=1):
+def cpu_baseline(args, log_n, repeats=1, time_budget_s=None):
     """Oracle C++ restatement of the reference prover (oracle/cport) on this box's host cores."""
     try:
         from oracle import cport
-        return cport.prover_baseline(args.curve, args.pc, args.cpu_log_n, repeats=repeats)
+        return cport.prover_baseline(args.curve, args.pc, log_n, repeats=repeats, time_budget_s=time_budget_s)
     except Exception as e:  # the baseline is reported, never required for the GPU number
         return {"value": None, "unit": "constraints/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU prover path (its C++/OpenMP restatement, oracle/cport -- the Rust
+    reference cannot be built in this image) on the SAME configuration as the GPU arm: Marlin::prove of DummyCircuit
+    2^log_n, all usable host threads, timed like benches/bench.rs:92-107 (prove only; SRS and index are set-up).  One
+    2^20 prove takes about a minute of CPU time, so the run is bounded by --ref-budget-s: `steps` reports the proves
+    actually timed (at least 1, at most --steps), `steps_requested` what the command line asked for."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t0 = time.time()
-    base = cpu_baseline(args, repeats=max(1, min(args.steps, 3)))  # index once, then `steps` (<= 3) full proves
+    log_n = args.ref_log_n if args.ref_log_n else args.log_n
+    base = cpu_baseline(args, log_n, repeats=max(1, args.steps), time_budget_s=args.ref_budget_s)
     v = base.get("value")
-    n = 1 << args.cpu_log_n
+    n = 1 << log_n
+    steps_run = base.get("steps_run", 0)
     line = {
         "impl": "reference", "metric": "prover_constraints_per_sec", "value": v, "unit": "constraints/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": (1000.0 * n / v) if v else None, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u32-limb modular integers (Fr 255-bit, Fq 381-bit)", "data": "synthetic",
-        "config": {"workload": f"Marlin::prove, DummyCircuit 2^{args.log_n} constraints, {args.curve}, {args.pc}",
-                   "sampled_on": f"2^{args.cpu_log_n} constraints (bounded CPU sample of the same circuit family)"},
+        "steps": steps_run, "steps_requested": args.steps, "warmup": 0, "warmup_requested": args.warmup,
+        "ms_per_step": (1000.0 * n / v) if v else None, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64-limb modular integers (Fr 255-bit, Fq 381-bit)", "data": "synthetic",
+        "config": {"workload": f"Marlin::prove, DummyCircuit 2^{log_n} constraints (|H|=2^{log_n}, |K|=2^{log_n + 2}), "
+                               f"{args.curve}, {args.pc}, SimpleHashFiatShamirRng<Blake2s,ChaChaRng>",
+                   "same_config_as_gpu_arm": log_n == args.log_n,
+                   "timing": f"wall clock around each prove; {steps_run} of {args.steps} requested steps fit the {args.ref_budget_s:.0f} s "
+                             "budget (no warm-up steps: a CPU prove has no cold-start effect worth a minute of budget)"},
         "cpu_baseline": dict(base or {}, value=v),
         "e2e": {"value": v, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.time() - t0,
@@ -172,7 +188,7 @@ def main():
     pk = m.index(srs, circ)
     setup_s = time.time() - t0
     m.stage(pk, circ)
-    zk = api.ZkRng()
+    zk = api.ZkRng.test_rng()
 
     def barrier():
         torch.cuda.synchronize()
@@ -216,14 +232,37 @@ def main():
     # outside every timed region: a proof from a fresh zk stream, hashed, so that runs with different window sizes,
     # GPU counts or library builds can be compared byte for byte
     import hashlib
-    proof_chk = m.prove(pk, circ, api.ZkRng())
+    proof_chk = m.prove(pk, circ, api.ZkRng.test_rng())
     proof_sha = hashlib.sha256(proof_chk).hexdigest()
-    if args.save_proof and rank == 0:
+    # ---- checker (outside every timed region; rank 0): the proof must be accepted by the oracle's restatement of
+    # Marlin::verify -- trapdoor identity AND the reference's real product of pairings -- rejected for a wrong public input,
+    # and equal to the pinned 1-GPU proof of the same instance where one is recorded (tests/golden/bench_proof_hashes.json).
+    proof_check, proof_verified, proof_matches = None, None, None
+    if rank == 0:
         from marlin_b200 import fields
-        with open(args.save_proof, "w") as f:
-            json.dump({"curve": args.curve, "pc": args.pc, "log_n": args.log_n, "n_gpus": world, "max_degree": int(srs.max_degree),
-                       "beta": 0x5eed5eed5eed5eed5eed5eed, "gamma": 7, "public_input": [str(a * b % fields.FR_MODULUS[cid])],
-                       "proof_hex": proof_chk.hex(), "vk_hex": bytes(pk.vk_bytes).hex(), "proof_sha256": proof_sha}, f)
+        blob = {"curve": args.curve, "pc": args.pc, "log_n": args.log_n, "n_gpus": world, "max_degree": int(srs.max_degree),
+                "beta": 0x5eed5eed5eed5eed5eed5eed, "gamma": 7, "public_input": [str(a * b % fields.FR_MODULUS[cid])],
+                "proof_hex": proof_chk.hex(), "vk_hex": bytes(pk.vk_bytes).hex(), "proof_sha256": proof_sha}
+        if args.save_proof:
+            with open(args.save_proof, "w") as f:
+                json.dump(blob, f)
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "bench_proof_hashes.json")) as f:
+                pinned = json.load(f).get(f"{args.curve}/{args.pc}/{args.log_n}")
+            proof_matches = (pinned == proof_sha) if pinned else None
+        except Exception:
+            pass
+        if not args.no_verify:
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                import verify_saved_proof
+                t_v = time.time()
+                proof_check = verify_saved_proof.verify_blob(blob, use_pairing=True)
+                proof_check["seconds"] = time.time() - t_v
+                proof_verified = bool(proof_check["ok"])
+            except Exception as e:
+                proof_check = {"error": repr(e)}
+                proof_verified = False
 
     ms_step = sum(dev_ms) / len(dev_ms)
     if dist is not None:  # max over ranks
@@ -296,10 +335,11 @@ def main():
                              "peak_source": "tools/microbench.cu fq_mul (measured on this pool's B200)"},
         "msm_bucket_pass_ms_per_step": bucket_ms / args.steps if bucket_ms else None,
         "kernels": kern, "phases_ms": phases, "dev_ms_steps": dev_ms, "setup_s": setup_s, "proof_bytes": len(proof), "proof_sha256": proof_sha,
+        "proof_verified": proof_verified, "proof_matches_pinned_1gpu_hash": proof_matches, "proof_check": proof_check,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args)
+            line["cpu_baseline"] = cpu_baseline(args, args.cpu_log_n, repeats=2, time_budget_s=30)
         print(json.dumps(line))
     pk.close()
     srs.close()

@@ -8,6 +8,7 @@ Every call lands in libb2m.so (include/b2m.h); nothing here computes on the CPU 
 """
 import ctypes
 import json
+import os
 
 import numpy as np
 
@@ -41,16 +42,26 @@ class Context:
 
 
 class ZkRng:
-    """The caller's `zk_rng` as a ChaCha stream position (ark_std::test_rng() = ChaCha12 with a fixed seed)."""
+    """The caller's `zk_rng` as a ChaCha stream position.  Like the reference, which makes the caller pass
+    `zk_rng: &mut R` [reference src/lib.rs:154], there is no implicit fixed seed: `ZkRng()` seeds from
+    os.urandom(32); the public `ark_std::test_rng()` stream (ChaCha12, fixed seed -- NOT zero-knowledge, every
+    blinding value is predictable) is only available through the explicit `ZkRng.test_rng()` used by tests
+    and the bench."""
     TEST_RNG_SEED = bytes([1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0] + [0] * 16)
 
     def __init__(self, seed=None, rounds=12, word_pos=0):
         self.c = _lib.Rng()
         self.c.kind = rounds
-        seed = self.TEST_RNG_SEED if seed is None else bytes(seed)
-        assert len(seed) == 32
+        seed = os.urandom(32) if seed is None else bytes(seed)
+        if len(seed) != 32:
+            raise ValueError("ZkRng seed must be 32 bytes")
         ctypes.memmove(self.c.key, seed, 32)
         self.c.word_pos = word_pos
+
+    @classmethod
+    def test_rng(cls):
+        """`ark_std::test_rng()`: rand 0.8 StdRng (ChaCha12) with the public fixed seed.  Tests / benchmarks only."""
+        return cls(cls.TEST_RNG_SEED, 12, 0)
 
     @property
     def word_pos(self):

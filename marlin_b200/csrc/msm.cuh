@@ -63,6 +63,8 @@ struct Msm {
   int affine_ctas_upper = 4;  // the same for levels >= 1 (streaming operands); B2M_MSM_AFFINE_CTAS_UPPER, 6 = two-chain ILP variant
   int affine_ctas = 4;      // level-kernel variant: resident CTAs per SM it is compiled for (B2M_MSM_AFFINE_CTAS: 3 = with prefetch, 4, 5)
   size_t affine_min_refs = MSM_AFFINE_MIN_REFS;  // B2M_MSM_AFFINE_MIN_REFS
+  int affine_map = 1;       // output -> thread mapping of the levels: 1 = warp-interleaved (coalesced), 0 = blocked; B2M_MSM_AFFINE_MAP
+  int affine_scr = 0;       // level 0 gathers its operands once into a thread-contiguous scratch; B2M_MSM_AFFINE_SCR
   int affine_T = 64;        // additions per thread and inversion in those levels; B2M_MSM_AFFINE_T
   int acc_ctas_per_sm = 3;  // resident CTAs of msm_accumulate_kernel per SM (occupancy query)
   DBuf<Affine<Fq>> tables;  // [W][stride]:  tables[w * stride + k] = 2^(c*w) * P_(k * world + rank)

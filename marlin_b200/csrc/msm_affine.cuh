@@ -45,7 +45,41 @@ struct AffLevel {
   Fq* pref;         // [T][nthreads] running denominator products
   uint4* meta;      // [T][nthreads] the plan: {P index | negate << 31, Q index | negate << 31, bucket, has Q}
   uint32_t T, nthreads;
+  // Output -> thread mapping.  lane_step == 1 ("blocked"): thread t owns the T consecutive outputs [t T, t T + T).
+  // lane_step == 32 ("interleaved", nthreads a multiple of 32): the 32 threads of a warp own 32 T consecutive outputs,
+  // lane l taking l, l + 32, l + 64, ... -- at every step the lanes of a warp then touch 32 ADJACENT outputs, so the
+  // level's output stores and (levels >= 1) its operand loads are whole contiguous runs (3 KB / 6 KB per warp and step)
+  // instead of 32 streams 6 KB apart, which DRAM sees as random 32-byte accesses.
+  uint32_t lane_step;
+  // level-0 operand scratch (SCR variants, else null): [T][2 * sizeof(Affine) / 16][nthreads] 16-byte chunks.  Pass 1
+  // gathers both operands of every output ONCE from the window tables (sign applied) and parks them here, thread-
+  // contiguous; pass 2 streams them back instead of gathering the same two random 96-byte points a second time.
+  uint4* opnd;
 };
+
+struct AffMap {
+  uint32_t o0, step, cnt;  // outputs o0 + k * step, k < cnt
+};
+template <class Fq>
+B2M_HD AffMap aff_map(const AffLevel<Fq>& A, uint32_t t, uint32_t total) {
+  AffMap m;
+  m.step = A.lane_step;
+  uint64_t o0;
+  if (A.lane_step == 1) {
+    o0 = (uint64_t)t * A.T;
+  } else {
+    o0 = (uint64_t)(t / A.lane_step) * A.lane_step * A.T + (t % A.lane_step);
+  }
+  if (o0 >= total) {
+    m.o0 = 0;
+    m.cnt = 0;
+    return m;
+  }
+  m.o0 = (uint32_t)o0;
+  const uint32_t left = (total - m.o0 + m.step - 1) / m.step;
+  m.cnt = left < A.T ? left : A.T;
+  return m;
+}
 
 #if defined(__CUDA_ARCH__)
 #define B2M_AFF_LDG(p) ldg_words(p)
@@ -75,22 +109,27 @@ B2M_HD uint32_t aff_bucket_of(const uint32_t* off, uint32_t n, uint32_t v) {
 template <class Fq, bool L0>
 B2M_HD void aff_plan_thread(const AffLevel<Fq>& A, uint32_t t) {
   const uint32_t total = B2M_AFF_LDG32(A.off_out + A.B);
-  const uint64_t o0_64 = (uint64_t)t * A.T;
-  if (o0_64 >= total) return;
-  const uint32_t o0 = (uint32_t)o0_64;
-  const uint32_t cnt = total - o0 < A.T ? total - o0 : A.T;
-  uint32_t b = aff_bucket_of(A.off_out, A.B, o0);
+  const AffMap mp = aff_map(A, t, total);
+  if (!mp.cnt) return;
+  uint32_t b = aff_bucket_of(A.off_out, A.B, mp.o0);
   uint32_t b_start = B2M_AFF_LDG32(A.off_out + b), b_end = B2M_AFF_LDG32(A.off_out + b + 1);
-  uint32_t in_start = B2M_AFF_LDG32(A.off_in + b), in_end = B2M_AFF_LDG32(A.off_in + b + 1);
-  for (uint32_t k = 0; k < cnt; k++) {
-    const uint32_t o = o0 + k;
-    while (o >= b_end) {  // next non-empty bucket
-      b++;
-      b_start = b_end;
-      b_end = B2M_AFF_LDG32(A.off_out + b + 1);
-      in_start = in_end;
-      in_end = B2M_AFF_LDG32(A.off_in + b + 1);
+  for (uint32_t k = 0; k < mp.cnt; k++) {
+    const uint32_t o = mp.o0 + k * mp.step;
+    if (o >= b_end) {
+      // next bucket holding `o`: a short walk (the common case: a few buckets ahead), else search -- a stride of 32
+      // outputs, or a run of empty buckets, can skip arbitrarily far
+      int steps = 0;
+      do {
+        b++;
+        b_end = B2M_AFF_LDG32(A.off_out + b + 1);
+      } while (o >= b_end && ++steps < 8);
+      if (o >= b_end) {
+        b = aff_bucket_of(A.off_out, A.B, o);
+        b_end = B2M_AFF_LDG32(A.off_out + b + 1);
+      }
+      b_start = B2M_AFF_LDG32(A.off_out + b);
     }
+    const uint32_t in_start = B2M_AFF_LDG32(A.off_in + b), in_end = B2M_AFF_LDG32(A.off_in + b + 1);
     const uint32_t i0 = in_start + 2u * (o - b_start);
     const bool pair = i0 + 1u < in_end;
     uint4 m;
@@ -148,25 +187,98 @@ B2M_HD AffKind aff_classify(const Affine<Fq>& P, const Affine<Fq>& Q, Fq* den) {
   return AFF_ADD;
 }
 
+// ---- operand scratch (SCR variants): element (k, t) is 2 * sizeof(Affine) / 16 chunks of 16 bytes, chunk-major so that a
+// warp's accesses to one chunk are 512 contiguous bytes --------------------------------------------------------------
+template <class Fq>
+B2M_HD void aff_opnd_store(uint4* opnd, size_t nth, uint32_t k, uint32_t t, const Affine<Fq>& P, const Affine<Fq>& Q) {
+  constexpr int CP = 2 * Fq::N / 4;  // 16-byte chunks per point
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(&P);
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(&Q);
+  uint4* dst = opnd + (size_t)k * (2 * CP) * nth + t;
+#pragma unroll
+  for (int c = 0; c < CP; c++) {
+    uint4 v;
+    v.x = p[4 * c]; v.y = p[4 * c + 1]; v.z = p[4 * c + 2]; v.w = p[4 * c + 3];
+    dst[(size_t)c * nth] = v;
+  }
+#pragma unroll
+  for (int c = 0; c < CP; c++) {
+    uint4 v;
+    v.x = q[4 * c]; v.y = q[4 * c + 1]; v.z = q[4 * c + 2]; v.w = q[4 * c + 3];
+    dst[(size_t)(CP + c) * nth] = v;
+  }
+}
+template <class Fq>
+B2M_HD void aff_opnd_load(const uint4* opnd, size_t nth, uint32_t k, uint32_t t, Affine<Fq>* P, Affine<Fq>* Q) {
+  constexpr int CP = 2 * Fq::N / 4;
+  uint32_t* p = reinterpret_cast<uint32_t*>(P);
+  uint32_t* q = reinterpret_cast<uint32_t*>(Q);
+  const uint4* src = opnd + (size_t)k * (2 * CP) * nth + t;
+#pragma unroll
+  for (int c = 0; c < CP; c++) {
+    const uint4 v = src[(size_t)c * nth];
+    p[4 * c] = v.x; p[4 * c + 1] = v.y; p[4 * c + 2] = v.z; p[4 * c + 3] = v.w;
+  }
+#pragma unroll
+  for (int c = 0; c < CP; c++) {
+    const uint4 v = src[(size_t)(CP + c) * nth];
+    q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
+  }
+}
+
 // ---- arithmetic: thread t adds the planned pairs of its T outputs with one shared inversion -----------------------
-// PF: load the next iteration's operands before the current iteration's multiplications (costs ~50 registers, so
-// fewer resident warps); without it the loads are issued at use and latency is hidden by occupancy alone.  The
-// random 96-byte gathers from the multi-GB window tables make these kernels latency / DRAM-page bound, and
-// memory-level parallelism from more resident warps measured better than prefetch depth.
-template <class Fq, bool PF>
+// PF = 1: load the next iteration's operands before the current iteration's multiplications in BOTH passes (costs ~50
+// registers, so fewer resident warps); PF = 2: in the denominator pass only (free: that pass is far below the register
+// high-water mark of the addition pass); PF = 0: loads are issued at use and latency is hidden by occupancy alone.
+// SCR (level 0): gather each operand once -- pass 1 loads the full points, parks them in A.opnd, pass 2 streams them.
+template <class Fq, int PF, bool SCR>
 B2M_HD void aff_level_thread(const AffLevel<Fq>& A, const Affine<Fq>* base, uint32_t t) {
   const uint32_t total = B2M_AFF_LDG32(A.off_out + A.B);
-  const uint64_t o0_64 = (uint64_t)t * A.T;
-  if (o0_64 >= total) return;
-  const uint32_t o0 = (uint32_t)o0_64;
-  const uint32_t cnt = total - o0 < A.T ? total - o0 : A.T;
+  const AffMap mp = aff_map(A, t, total);
+  if (!mp.cnt) return;
+  const uint32_t cnt = mp.cnt;
   const size_t nth = A.nthreads;
   const uint4* meta = A.meta + t;
   Fq* pref = A.pref + t;
   // ---- pass 1: denominators, running product ----------------------------------------------------
   Fq run = Fq::one();
-  bool any = false;
-  {
+  if (SCR) {
+    uint4 m = meta[0];
+    Affine<Fq> Pn, Qn;
+    if (PF) {
+      Pn = aff_ld(base, m.x);
+      Qn = aff_ld(base, m.y);
+    }
+    for (uint32_t k = 0; k < cnt; k++) {
+      const uint4 mc = m;
+      Affine<Fq> P, Q;
+      if (PF) {
+        P = Pn;
+        Q = Qn;
+      } else {
+        P = aff_ld(base, mc.x);
+        Q = aff_ld(base, mc.y);
+      }
+      if (k + 1 < cnt) {
+        m = meta[(size_t)(k + 1) * nth];
+        if (PF) {
+          Pn = aff_ld(base, m.x);
+          Qn = aff_ld(base, m.y);
+        }
+      }
+      P = aff_signed(P, mc.x);
+      Q = aff_signed(Q, mc.y);
+      aff_opnd_store(A.opnd, nth, k, t, P, Q);
+      Fq den = Fq::one();
+      if (mc.w) {
+        Fq d;
+        const AffKind kind = aff_classify(P, Q, &d);
+        if (kind == AFF_ADD || kind == AFF_DBL) den = d;
+      }
+      run = k ? run * den : den;
+      B2M_AFF_ST(pref + (size_t)k * nth, run);
+    }
+  } else {
     uint4 m = meta[0];
     uint4 m1 = cnt > 1 ? meta[nth] : m;
     Fq x1, x2;
@@ -192,32 +304,30 @@ B2M_HD void aff_level_thread(const AffLevel<Fq>& A, const Affine<Fq>* base, uint
           x2 = aff_ldx(base, m.y);
         }
       }
+      Fq den = Fq::one();
       if (mc.w) {
-        Fq den;
-        bool has = true;
         if (c1.is_zero() || c2.is_zero() || c1 == c2) {  // rare: infinity, doubling or cancellation
-          const AffKind kind = aff_classify(aff_signed(aff_ld(base, mc.x), mc.x), aff_signed(aff_ld(base, mc.y), mc.y), &den);
-          has = kind == AFF_ADD || kind == AFF_DBL;
+          Fq d;
+          const AffKind kind = aff_classify(aff_signed(aff_ld(base, mc.x), mc.x), aff_signed(aff_ld(base, mc.y), mc.y), &d);
+          if (kind == AFF_ADD || kind == AFF_DBL) den = d;
         } else {
           den = c2 - c1;
         }
-        if (has) {
-          run = any ? run * den : den;
-          any = true;
-        }
       }
+      run = k ? run * den : den;
       B2M_AFF_ST(pref + (size_t)k * nth, run);
     }
   }
-  // ---- one inversion per thread -------------------------------------------------------------------
-  Fq inv = any ? run.inverse_fast() : run;
+  // ---- one inversion per thread (the product of non-zero denominators is never zero) -----------------
+  Fq inv = run.inverse_fast();
   // ---- pass 2: walk back, peel one denominator at a time ----------------------------------------------
   {
+    constexpr bool PF2 = PF == 1 && !SCR;
     uint4 m = meta[(size_t)(cnt - 1) * nth];
     uint4 m1 = cnt > 1 ? meta[(size_t)(cnt - 2) * nth] : m;
     Affine<Fq> Pn, Qn;
     Fq pfn = run;  // product of the denominators before the output (read for k > 0 only)
-    if (PF) {
+    if (PF2) {
       Pn = aff_ld(base, m.x);
       Qn = aff_ld(base, m.y);
       if (cnt > 1) pfn = B2M_AFF_LD(pref + (size_t)(cnt - 2) * nth);
@@ -226,21 +336,27 @@ B2M_HD void aff_level_thread(const AffLevel<Fq>& A, const Affine<Fq>* base, uint
       const uint4 mc = m;
       Affine<Fq> P, Q;
       Fq pf = run;
-      if (PF) {
+      if (PF2) {
         P = Pn;
         Q = Qn;
         pf = pfn;
       } else {
-        P = aff_ld(base, mc.x);
-        Q = aff_ld(base, mc.y);
+        if (SCR) {
+          aff_opnd_load(A.opnd, nth, k, t, &P, &Q);
+        } else {
+          P = aff_ld(base, mc.x);
+          Q = aff_ld(base, mc.y);
+        }
         if (k > 0) pf = B2M_AFF_LD(pref + (size_t)(k - 1) * nth);
       }
-      P = aff_signed(P, mc.x);
-      Q = aff_signed(Q, mc.y);
+      if (!SCR) {  // (the scratch holds the points with the sign applied)
+        P = aff_signed(P, mc.x);
+        Q = aff_signed(Q, mc.y);
+      }
       if (k > 0) {
         m = m1;
         if (k > 1) m1 = meta[(size_t)(k - 2) * nth];
-        if (PF) {
+        if (PF2) {
           Pn = aff_ld(base, m.x);
           Qn = aff_ld(base, m.y);
           if (k > 1) pfn = B2M_AFF_LD(pref + (size_t)(k - 2) * nth);
@@ -270,7 +386,7 @@ B2M_HD void aff_level_thread(const AffLevel<Fq>& A, const Affine<Fq>* base, uint
           R.y = lam * (P.x - R.x) - P.y;
         }
       }
-      const uint32_t o = o0 + k;
+      const uint32_t o = mp.o0 + k * mp.step;
       B2M_AFF_ST(&A.out[o].x, R.x);
       B2M_AFF_ST(&A.out[o].y, R.y);
       if (A.out_refs) {
@@ -338,10 +454,9 @@ B2M_HD void aff_store_out(const AffLevel<Fq>& A, uint32_t o, const Affine<Fq>& R
 template <class Fq>
 B2M_HD void aff_level_thread_ilp(const AffLevel<Fq>& A, const Affine<Fq>* base, uint32_t t) {
   const uint32_t total = B2M_AFF_LDG32(A.off_out + A.B);
-  const uint64_t o0_64 = (uint64_t)t * A.T;
-  if (o0_64 >= total) return;
-  const uint32_t o0 = (uint32_t)o0_64;
-  const uint32_t cnt = total - o0 < A.T ? total - o0 : A.T;
+  const AffMap mp = aff_map(A, t, total);
+  if (!mp.cnt) return;
+  const uint32_t cnt = mp.cnt;
   const size_t nth = A.nthreads;
   const uint4* meta = A.meta + t;
   Fq* pref = A.pref + t;
@@ -374,7 +489,7 @@ B2M_HD void aff_level_thread_ilp(const AffLevel<Fq>& A, const Affine<Fq>* base, 
     Fq den;
     const Affine<Fq> R = aff_finish(P, Q, m.w != 0, dinv, &den);
     inv0 = inv0 * den;
-    aff_store_out(A, o0 + k, R, m.z);
+    aff_store_out(A, mp.o0 + k * mp.step, R, m.z);
   }
   while (k >= 2) {
     k -= 2;  // outputs k + 1 (odd chain) and k (even chain)
@@ -390,8 +505,8 @@ B2M_HD void aff_level_thread_ilp(const AffLevel<Fq>& A, const Affine<Fq>* base, 
     const Affine<Fq> R0 = aff_finish(P0, Q0, m0.w != 0, dinv0, &den0);
     inv1 = inv1 * den1;
     inv0 = inv0 * den0;
-    aff_store_out(A, o0 + k + 1, R1, m1.z);
-    aff_store_out(A, o0 + k, R0, m0.z);
+    aff_store_out(A, mp.o0 + (k + 1) * mp.step, R1, m1.z);
+    aff_store_out(A, mp.o0 + k * mp.step, R0, m0.z);
   }
 }
 

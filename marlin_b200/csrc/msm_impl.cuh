@@ -198,10 +198,10 @@ __global__ void __launch_bounds__(256) msm_affine_plan_kernel(const AffLevel<Fq>
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < A.nthreads) aff_plan_thread<Fq, L0>(A, t);
 }
-template <class Fq, int MINB, bool PF>
+template <class Fq, int MINB, int PF, bool SCR>
 __global__ void __launch_bounds__(128, MINB) msm_affine_level_kernel(const AffLevel<Fq> A, const Affine<Fq>* __restrict__ base) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < A.nthreads) aff_level_thread<Fq, PF>(A, base, t);
+  if (t < A.nthreads) aff_level_thread<Fq, PF, SCR>(A, base, t);
 }
 
 // opt-in two-chain variant (msm_affine.cuh aff_level_thread_ilp): B2M_MSM_AFFINE_CTAS / B2M_MSM_AFFINE_CTAS_UPPER = 6
@@ -475,6 +475,8 @@ Msm<Fr, Fq>::Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, const Affine<
   affine_ctas_upper = affine_ctas;
   if (const char* e = getenv("B2M_MSM_AFFINE_CTAS_UPPER")) affine_ctas_upper = atoi(e);
   if (const char* e = getenv("B2M_MSM_AFFINE_MIN_REFS")) affine_min_refs = (size_t)atoll(e);
+  if (const char* e = getenv("B2M_MSM_AFFINE_MAP")) affine_map = atoi(e);
+  if (const char* e = getenv("B2M_MSM_AFFINE_SCR")) affine_scr = atoi(e);
   if (affine_levels < 0) affine_levels = 0;
   if (affine_levels > MSM_MAX_AFFINE_LEVELS) affine_levels = MSM_MAX_AFFINE_LEVELS;
   if (affine_T < 1) affine_T = 1;
@@ -531,6 +533,8 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
     B2M_REQUIRE(jobs[j].n2 == 0 || jobs[j].extra_base + jobs[j].n2 <= n_extra, B2M_ERR_INVALID_ARG, "extra bases out of range");
     max_n = std::max(max_n, jobs[j].n + jobs[j].n2);
   }
+  // 32-bit positions: the sorted references, their offsets and the per-thread ranges index W * n references
+  B2M_REQUIRE((size_t)W * max_n < ((size_t)1 << 32), B2M_ERR_DEGREE_TOO_LARGE, "MSM of %zu pairs x %d windows exceeds 2^32 bucket references", max_n, W);
   MsmFinishJobs fj;
   for (int j = 0; j < nj; j++) fj.j[j] = MsmFinishJob{jobs[j].extra, jobs[j].n_extra, jobs[j].out_xyzz, jobs[j].out_affine};
   auto exchange = [&]() {  // multi-GPU: gather the per-rank partial sums and fold them (plus the extras) on every rank
@@ -574,22 +578,26 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
     DBuf<XYZZ<Fq>> part_pt(cx, 2 * max_threads);
     // batched-affine levels (msm_affine.cuh): level l has at most bound[l] points
     const int LV = max_refs >= affine_min_refs ? affine_levels : 0;  // (the largest job of the batch decides the buffers)
+    // the level-0 plan packs (window * stride + index) | sign << 31 into 32 bits (msm_affine.cuh aff_plan_thread)
+    B2M_REQUIRE(LV == 0 || (size_t)W * stride < ((size_t)1 << 31), B2M_ERR_DEGREE_TOO_LARGE,
+                "window tables of %d x %zu entries exceed the 31-bit index of the batched-affine plan", W, stride);
     size_t bound[MSM_MAX_AFFINE_LEVELS + 1];
     bound[0] = max_refs;
     for (int l = 1; l <= LV; l++) bound[l] = (bound[l - 1] + B) / 2 + 1;
     DBuf<Affine<Fq>> lvl_pts[2];
     DBuf<uint32_t> lvl_off[2], lvl_cnt;
     DBuf<uint2> lvl_refs;
-    DBuf<uint4> lvl_meta;
+    DBuf<uint4> lvl_meta, lvl_opnd;
     DBuf<Fq> lvl_pref;
     if (LV > 0) {
       lvl_pts[0] = DBuf<Affine<Fq>>(cx, bound[1]);
       if (LV > 1) lvl_pts[1] = DBuf<Affine<Fq>>(cx, bound[2]);
       lvl_off[0] = DBuf<uint32_t>(cx, B + 1); lvl_off[1] = DBuf<uint32_t>(cx, B + 1); lvl_cnt = DBuf<uint32_t>(cx, B + 1);
       lvl_refs = DBuf<uint2>(cx, bound[LV]);
-      const size_t slots_l0 = (size_t)affine_T * ((bound[1] + affine_T - 1) / affine_T + 128);
+      const size_t slots_l0 = (size_t)affine_T * ((bound[1] + affine_T - 1) / affine_T + 128);  // >= T * nthreads for either mapping
       lvl_meta = DBuf<uint4>(cx, slots_l0);
       lvl_pref = DBuf<Fq>(cx, slots_l0);
+      if (affine_scr) lvl_opnd = DBuf<uint4>(cx, slots_l0 * (2 * sizeof(Affine<Fq>) / 16));
     }
     buckets.zero();  // empty buckets are never written: all-zero XYZZ is the point at infinity
     cudaEvent_t ev_ready, ev_sorted[MSM_MAX_BATCH], ev_acc[MSM_MAX_BATCH];
@@ -643,21 +651,37 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
           B2M_CHECK_LAUNCH();
           cx.launches++;
           exclusive_scan_u32(cx, lvl_cnt.p, off_out, (size_t)B + 1);
-          const uint32_t nthreads = (uint32_t)((bound[l + 1] + affine_T - 1) / affine_T);
+          const uint32_t lane_step = affine_map ? 32u : 1u;
+          const uint32_t nthreads = (uint32_t)(lane_step * ((bound[l + 1] + (size_t)lane_step * affine_T - 1) / ((size_t)lane_step * affine_T)));
+          const bool scr = l == 0 && affine_scr;
           AffLevel<Fq> A{tables.p, stride, sorted[s].p, l > 0 ? lvl_pts[(l - 1) & 1].p : nullptr, off_in, off_out, B, lvl_pts[l & 1].p,
-                         l == LV - 1 ? lvl_refs.p : nullptr, lvl_pref.p, lvl_meta.p, (uint32_t)affine_T, nthreads};
+                         l == LV - 1 ? lvl_refs.p : nullptr, lvl_pref.p, lvl_meta.p, (uint32_t)affine_T, nthreads, lane_step,
+                         scr ? lvl_opnd.p : nullptr};
           if (l == 0)
             msm_affine_plan_kernel<Fq, true><<<div_up(nthreads, 256), 256, 0, cx.stream>>>(A);
           else
             msm_affine_plan_kernel<Fq, false><<<div_up(nthreads, 256), 256, 0, cx.stream>>>(A);
           const Affine<Fq>* base = l == 0 ? tables.p : lvl_pts[(l - 1) & 1].p;
           const unsigned grid = div_up(nthreads, 128);
-          switch (l == 0 ? affine_ctas : affine_ctas_upper) {  // kernel variant: resident CTAs per SM it is compiled for
-            case 6: msm_affine_level_ilp_kernel<Fq><<<grid, 128, 0, cx.stream>>>(A, base); break;  // two chains, 2 CTAs/SM
-            case 3:  // with operand prefetch msm_affine_level_kernel<Fq, 3, true><<<grid, 128, 0, cx.stream>>>(A, base); break;
-            case 5: msm_affine_level_kernel<Fq, 5, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
-            default: msm_affine_level_kernel<Fq, 4, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
+          // kernel variant: 4 (default) / 5 = plain loads, compiled for that many resident CTAs per SM; 3 = operands
+          // prefetched in both passes (3 CTAs/SM); 7 = prefetched in the denominator pass only; 6 = two chains (ILP)
+          const int variant = l == 0 ? affine_ctas : affine_ctas_upper;
+          static const char* const lvl_names[MSM_MAX_AFFINE_LEVELS] = {"msm_aff_level0", "msm_aff_level1", "msm_aff_level2", "msm_aff_level3",
+                                                                       "msm_aff_level4", "msm_aff_level5"};
+          const size_t spk = cx.span_begin(lvl_names[l], (double)n);
+          if (scr) {
+            if (variant == 7) msm_affine_level_kernel<Fq, 4, 2, true><<<grid, 128, 0, cx.stream>>>(A, base);
+            else msm_affine_level_kernel<Fq, 4, 0, true><<<grid, 128, 0, cx.stream>>>(A, base);
+          } else {
+            switch (variant) {
+              case 6: msm_affine_level_ilp_kernel<Fq><<<grid, 128, 0, cx.stream>>>(A, base); break;
+              case 3: msm_affine_level_kernel<Fq, 3, 1, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
+              case 5: msm_affine_level_kernel<Fq, 5, 0, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
+              case 7: msm_affine_level_kernel<Fq, 4, 2, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
+              default: msm_affine_level_kernel<Fq, 4, 0, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
+            }
           }
+          cx.span_end(spk);
           B2M_CHECK_LAUNCH();
           cx.launches += 2;
           off_in = off_out;

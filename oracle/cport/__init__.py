@@ -24,6 +24,8 @@ def lib():
         L.cport_fft.argtypes = [ci, vp, ctypes.c_uint, ci, ci]
         L.cport_gen_bases.argtypes = [ci, vp, sz, vp]
         L.cport_max_threads.restype = ci
+        L.cport_set_skip_index_commit.argtypes = [ci]
+        L.cport_set_skip_index_commit.restype = None
         u8p = ctypes.c_void_p
         L.cport_index_create.argtypes = [ci, ci, ci, vp, sz, vp, vp, sz, sz, sz, sz] + [vp] * 9 + [ctypes.POINTER(ctypes.c_void_p)]
         L.cport_index_free.argtypes = [vp]
@@ -157,12 +159,29 @@ class CpuProver:
             self.h = None
 
 
-def prover_baseline(curve_name, pc, log_n, threads=0, repeats=1):
-    """CPU baseline for bench.py: the C++ restatement of the reference prover (prover.cpp) timed on one
-    `Marlin::prove` of the reference bench's DummyCircuit with 2^log_n constraints (index and SRS excluded, like
-    benches/bench.rs).  The SRS used for timing is a set of distinct curve points ((i + 1) * G), not powers of a
-    trapdoor: the work is identical, the proof is not meant to verify."""
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def prover_baseline(curve_name, pc, log_n, threads=0, repeats=1, time_budget_s=None, skip_index_commit=True):
+    """CPU baseline for bench.py: the C++ restatement of the reference prover (prover.cpp) timed on `Marlin::prove` of the
+    reference bench's DummyCircuit with 2^log_n constraints (index and SRS excluded, like benches/bench.rs:79-107).
+    Runs up to `repeats` proves, stopping early once `time_budget_s` (set-up included) would be exceeded; at least one.
+    The SRS used for timing is a set of distinct curve points ((i + 1) * G), not powers of a trapdoor, and (by default) the
+    six index commitments -- set-up work outside the timed region -- are skipped: the work of `prove` is identical, the
+    proof is not meant to verify.  The OpenMP team size is set explicitly (usable_cpus()), so a launcher's
+    OMP_NUM_THREADS=1 (torchrun) cannot turn the baseline single-threaded."""
+    import time
     from marlin_b200 import _lib as plib, fields, r1cs as gr1cs  # host-side marshalling helpers only (no GPU code runs)
+    t_start = time.time()
+    L = lib()
+    L.cport_set_skip_index_commit(1 if skip_index_commit else 0)
     cid = CURVE_ID[curve_name]
     n = 1 << log_n
     D = 4 * n - 1
@@ -170,22 +189,31 @@ def prover_baseline(curve_name, pc, log_n, threads=0, repeats=1):
     g = fields.G1_GENERATOR[cid]
     g_l = plib.ints_to_limbs([fields.fq_to_mont(cid, g[0]), fields.fq_to_mont(cid, g[1])], lq).reshape(1, 2 * lq)
     powers = np.zeros((D + 1, 2 * lq), dtype=np.uint64)
-    lib().cport_gen_bases(cid, _ptr(g_l), D + 1, _ptr(powers))
+    L.cport_gen_bases(cid, _ptr(g_l), D + 1, _ptr(powers))
     gidx = sorted({0, 1, 2} | {D - d + i for d in (n - 2, 4 * n - 2) for i in range(3) if D - d + i <= D})
     gam = np.ascontiguousarray(powers[gidx])
     circ = gr1cs.dummy_circuit(cid, 0x1234567890abcdef, 0xfedcba0987654321, 10, n)
-    cp = CpuProver(curve_name, pc, powers, gam, gidx, circ.num_constraints, circ.num_variables, circ.num_instance, circ.a, circ.b, circ.c, threads)
+    nthreads = threads or min(usable_cpus(), L.cport_max_threads())
+    try:
+        cp = CpuProver(curve_name, pc, powers, gam, gidx, circ.num_constraints, circ.num_variables, circ.num_instance, circ.a, circ.b, circ.c,
+                       nthreads)
+    finally:
+        L.cport_set_skip_index_commit(0)
+    setup_s = time.time() - t_start
     try:
         secs = []
         pos = 0
         for _ in range(max(1, repeats)):
+            if secs and time_budget_s is not None and (time.time() - t_start) + max(secs) > time_budget_s:
+                break
             _, pos, s = cp.prove(circ.instance, circ.witness, bytes(range(32)), 12, pos)
             secs.append(s)
-        best = sum(secs) / len(secs)
-        return {"value": n / best, "unit": "constraints/s", "cores": cp.threads, "kind": "port",
+        mean = sum(secs) / len(secs)
+        return {"value": n / mean, "unit": "constraints/s", "cores": cp.threads, "kind": "port", "cpu": cpu_model(),
                 "sample": (f"C++/OpenMP restatement of the reference prover (oracle/cport/prover.cpp: ark-ec Pippenger with one task per "
-                           f"window, radix-2 FFTs, the reference's round structure), one full Marlin::prove ({pc}) of DummyCircuit "
-                           f"2^{log_n} = {best:.2f} s on {cp.threads} threads (bounded sample of the 2^20 workload)"),
-                "seconds": best}
+                           f"window, radix-2 FFTs, the reference's round structure): {len(secs)} full Marlin::prove ({pc}, {curve_name}) of "
+                           f"DummyCircuit 2^{log_n}, mean {mean:.2f} s on {cp.threads} threads; set-up (SRS points, index) {setup_s:.0f} s "
+                           f"outside the timed region"),
+                "seconds": mean, "seconds_per_step": secs, "steps_run": len(secs), "log_n": log_n, "setup_s": setup_s}
     finally:
         cp.close()

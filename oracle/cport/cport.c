@@ -16,14 +16,14 @@ int cport_gen_bases(int curve, const u64* g_xy, size_t n, u64* out) {
     bls_aff g; memcpy(&g, g_xy, sizeof(g)); bls_jac acc; bls_jac_set_inf(&acc); bls_aff* o = (bls_aff*)out;
     bls_jac* tmp = (bls_jac*)malloc(sizeof(bls_jac) * n);
     for (size_t i = 0; i < n; i++) { bls_add_mixed(&acc, &g, &BLS_FQ); tmp[i] = acc; }
-    #pragma omp parallel for
+    #pragma omp parallel for num_threads(max_threads())
     for (size_t i = 0; i < n; i++) bls_to_affine(&o[i], &tmp[i], &BLS_FQ);
     free(tmp);
   } else {
     bn_aff g; memcpy(&g, g_xy, sizeof(g)); bn_jac acc; bn_jac_set_inf(&acc); bn_aff* o = (bn_aff*)out;
     bn_jac* tmp = (bn_jac*)malloc(sizeof(bn_jac) * n);
     for (size_t i = 0; i < n; i++) { bn_add_mixed(&acc, &g, &BN_FQ); tmp[i] = acc; }
-    #pragma omp parallel for
+    #pragma omp parallel for num_threads(max_threads())
     for (size_t i = 0; i < n; i++) bn_to_affine(&o[i], &tmp[i], &BN_FQ);
     free(tmp);
   }

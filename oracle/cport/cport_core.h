@@ -68,9 +68,12 @@ static void init_all(void) {
   inited = 1;
 }
 static double now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+/* Processors this process may run on -- NOT omp_get_max_threads(): launchers such as torchrun export OMP_NUM_THREADS=1,
+ * which would silently turn the baseline single-threaded.  Every parallel region below names its team size explicitly. */
 static int max_threads(void) {
 #ifdef _OPENMP
-  return omp_get_max_threads();
+  omp_set_dynamic(0);
+  return omp_get_num_procs();
 #else
   return 1;
 #endif

@@ -17,7 +17,8 @@ SO = os.path.join(HERE, "host", "libfield_host.so")
 @pytest.fixture(scope="module")
 def hostlib():
     src = os.path.join(HERE, "host", "field_host_shim.cpp")
-    if not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(src):
+    deps = [src] + [os.path.join(HERE, "..", "marlin_b200", "csrc", h) for h in ("field.cuh", "curve.cuh", "msm_affine.cuh")]
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", src, "-o", SO])
     return ctypes.CDLL(SO)
 
@@ -144,14 +145,20 @@ def test_batched_affine_levels(hostlib, ci, curve):
             want.append(acc)
         refs_a = np.array(refs if refs else [0, 0], dtype=np.uint32)
         off_a = np.array(off, dtype=np.uint32)
-        # variant 0: default thread function (odd T: with operand prefetch), variant 1: the two-chain ILP one
-        for levels, T, variant in ((0, 1, 0), (1, 1, 0), (1, 4, 0), (2, 3, 0), (3, 8, 0), (4, 2, 0), (7, 5, 0), (3, 64, 0),
-                                   (1, 1, 1), (1, 2, 1), (2, 3, 1), (3, 8, 1), (4, 5, 1), (7, 4, 1), (3, 64, 1), (2, 7, 1)):
+        # variant 0: default thread function (odd T: with operand prefetch), 1: the two-chain ILP one, 2: prefetch in the
+        # denominator pass only; mapping 0 = blocked, 1 = warp-interleaved; scr = level 0 parks its operands in the scratch
+        cases = [(0, 1, 0, 0, 0), (1, 1, 0, 0, 0), (1, 4, 0, 0, 0), (2, 3, 0, 0, 0), (3, 8, 0, 0, 0), (7, 5, 0, 0, 0), (3, 64, 0, 0, 0),
+                 (1, 1, 1, 0, 0), (2, 3, 1, 0, 0), (3, 8, 1, 0, 0), (4, 5, 1, 0, 0), (3, 64, 1, 0, 0),
+                 (1, 1, 0, 1, 0), (1, 4, 0, 1, 0), (2, 3, 0, 1, 0), (3, 2, 0, 1, 0), (4, 1, 2, 1, 0), (3, 8, 2, 1, 0), (7, 5, 0, 1, 0),
+                 (2, 3, 1, 1, 0), (3, 2, 1, 1, 0), (4, 5, 1, 1, 0), (3, 64, 1, 1, 0),
+                 (1, 1, 0, 1, 1), (2, 2, 0, 1, 1), (3, 3, 0, 1, 1), (3, 4, 2, 0, 1), (4, 1, 1, 1, 1), (3, 8, 0, 0, 1)]
+        for levels, T, variant, interleaved, scr in cases:
             out = np.zeros(B * 2 * n32, dtype=np.uint32)
             hostlib.affine_levels_host(ci, tab_l.ctypes.data_as(ctypes.c_void_p), refs_a.ctypes.data_as(ctypes.c_void_p),
-                                       off_a.ctypes.data_as(ctypes.c_void_p), B, levels, T, out.ctypes.data_as(ctypes.c_void_p), variant)
+                                       off_a.ctypes.data_as(ctypes.c_void_p), B, levels, T, out.ctypes.data_as(ctypes.c_void_p), variant,
+                                       interleaved, scr)
             for b in range(B):
                 x = sum(int(out[b * 2 * n32 + i]) << (32 * i) for i in range(n32))
                 y = sum(int(out[b * 2 * n32 + n32 + i]) << (32 * i) for i in range(n32))
                 got = None if x == 0 and y == 0 else (fq.from_mont(x), fq.from_mont(y))
-                assert got == want[b], (trial, levels, T, variant, b)
+                assert got == want[b], (trial, levels, T, variant, interleaved, scr, b)

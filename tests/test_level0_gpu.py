@@ -189,14 +189,21 @@ def test_msm_skewed_scalars(b2m_ctx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("levels,T,variant", [(1, 1, 4), (2, 3, 4), (3, 64, 4), (4, 5, 3), (6, 2, 5)])
-def test_msm_affine_levels_forced(b2m_ctx, monkeypatch, levels, T, variant):
+@pytest.mark.parametrize("levels,T,variant,upper,mapping,scr", [
+    (1, 1, 4, 4, 1, 0), (2, 3, 4, 4, 1, 0), (3, 64, 4, 4, 1, 0), (4, 5, 3, 3, 1, 0), (6, 2, 5, 5, 1, 0),  # every kernel variant, default mapping
+    (3, 4, 6, 6, 1, 0), (2, 7, 6, 4, 1, 0), (3, 64, 4, 6, 1, 0), (3, 5, 7, 7, 1, 0),                      # two-chain (ILP), pass-1 prefetch
+    (3, 64, 4, 4, 1, 1), (2, 3, 7, 4, 1, 1), (4, 1, 4, 6, 1, 1),                                           # level 0 through the operand scratch
+    (3, 64, 4, 4, 0, 0), (2, 5, 6, 6, 0, 0), (3, 3, 3, 7, 0, 1)])                                          # blocked mapping
+def test_msm_affine_levels_forced(b2m_ctx, monkeypatch, levels, T, variant, upper, mapping, scr):
     """The batched-affine levels (csrc/msm_affine.cuh) are skipped for small MSMs; force them on (any size, odd
     batch lengths, every kernel variant) over the inputs that hit their special cases: colliding bases (P + P,
     P - P inside a bucket, at level 0 and above), zero / equal / tiny scalars, buckets of every parity."""
     monkeypatch.setenv("B2M_MSM_AFFINE_LEVELS", str(levels))
     monkeypatch.setenv("B2M_MSM_AFFINE_T", str(T))
     monkeypatch.setenv("B2M_MSM_AFFINE_CTAS", str(variant))
+    monkeypatch.setenv("B2M_MSM_AFFINE_CTAS_UPPER", str(upper))
+    monkeypatch.setenv("B2M_MSM_AFFINE_MAP", str(mapping))
+    monkeypatch.setenv("B2M_MSM_AFFINE_SCR", str(scr))
     monkeypatch.setenv("B2M_MSM_AFFINE_MIN_REFS", "0")
     curve = BLS12_381
     r = curve.fr.p

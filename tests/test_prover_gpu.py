@@ -126,7 +126,7 @@ def test_error_codes(gctx):
         pk = m.index(srs, small)
         other = gr1cs.dummy_circuit(0, 3, 4, 10, 8)
         with pytest.raises(_lib.B2MError) as e:
-            m.prove(pk, other, api.ZkRng())
+            m.prove(pk, other, api.ZkRng.test_rng())
         assert e.value.code == 3  # B2M_ERR_INSTANCE_MISMATCH
         pk.close()
     finally:
@@ -188,7 +188,9 @@ def test_golden_fixture_bytes(gctx, case):
 
 
 @pytest.mark.parametrize("curve_name,log_n,scheme", [("bls12_381", 16, "marlin_kzg10"), ("bls12_381", 16, "sonic_kzg10"),
-                                                     ("bn254", 16, "marlin_kzg10"), ("bls12_381", 20, "marlin_kzg10")])
+                                                     ("bn254", 16, "marlin_kzg10"), ("bls12_381", 20, "marlin_kzg10"),
+                                                     ("bn254", 20, "marlin_kzg10"),       # BASELINE.json config 4 at full size
+                                                     ("bls12_381", 22, "sonic_kzg10")])   # BASELINE.json config 3 at full size
 def test_full_size_proof_verifies(gctx, curve_name, log_n, scheme):
     """Size-independent check at BASELINE.json's sizes (the oracle cannot *prove* 2^20 in reasonable time, but
     verification needs only public data): the GPU proof of a 2^log_n-constraint DummyCircuit is accepted by the
@@ -207,7 +209,7 @@ def test_full_size_proof_verifies(gctx, curve_name, log_n, scheme):
     try:
         pk = m.index(srs, circ)
         try:
-            proof_bytes = m.prove(pk, circ, api.ZkRng())
+            proof_bytes = m.prove(pk, circ, api.ZkRng.test_rng())
             comms = util.points_from_limbs(curve, pk.index_comms)
             lazy = kzg.UniversalParams(curve, srs.max_degree, beta, curve.g, gamma, powers_of_g="lazy")
             vk = omarlin.verifier_key_from_public(curve, SCHEMES[scheme], lazy, n, n, 3 * (n - 1), comms)
@@ -276,7 +278,9 @@ def ec_scalar(curve, k):
     return ec.scalar_mul(curve, k, curve.g)
 
 
-@pytest.mark.parametrize("curve_name,scheme,log_n", [("bls12_381", "marlin_kzg10", 14), ("bls12_381", "sonic_kzg10", 14), ("bn254", "marlin_kzg10", 13)])
+@pytest.mark.parametrize("curve_name,scheme,log_n", [("bls12_381", "marlin_kzg10", 14), ("bls12_381", "sonic_kzg10", 14), ("bn254", "marlin_kzg10", 13),
+                                                     ("bn254", "marlin_kzg10", 16), ("bls12_381", "sonic_kzg10", 16),
+                                                     ("bls12_381", "marlin_kzg10", 20)])  # BASELINE.json config 2, byte for byte (~3 CPU-minutes)
 def test_bytes_match_cpp_cpu_prover(gctx, curve_name, scheme, log_n):
     """Byte-exact parity at sizes the Python oracle cannot prove: the same GPU-generated SRS, the same instance and
     RNG seed go to libb2m (CUDA) and to oracle/cport/prover.cpp (the C++ restatement of the reference prover, itself
@@ -292,15 +296,25 @@ def test_bytes_match_cpp_cpu_prover(gctx, curve_name, scheme, log_n):
     try:
         pk = m.index(srs, circ)
         try:
-            rng = api.ZkRng(bytes(range(32)), 12)
+            # the BASELINE-size case uses bench.py's zk stream (ark_std::test_rng) so that the proof bench.py hashes -- and
+            # pins in tests/golden/bench_proof_hashes.json -- is the very proof compared with the C++ prover here
+            seed = api.ZkRng.TEST_RNG_SEED if log_n >= 20 else bytes(range(32))
+            rng = api.ZkRng(seed, 12)
             gproof = m.prove(pk, circ, rng)
             cp = cport.CpuProver(curve_name, scheme, srs.powers_limbs, srs.gamma_limbs, srs.gamma_indices, circ.num_constraints,
                                  circ.num_variables, circ.num_instance, circ.a, circ.b, circ.c)
             try:
                 assert cp.vk_bytes == pk.vk_bytes
-                cproof, pos, _ = cp.prove(circ.instance, circ.witness, bytes(range(32)), 12, 0)
+                cproof, pos, _ = cp.prove(circ.instance, circ.witness, seed, 12, 0)
                 assert cproof == gproof
                 assert pos == rng.word_pos
+                if log_n >= 20:
+                    import hashlib
+                    import json
+                    import os
+                    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bench_proof_hashes.json")) as fh:
+                        pinned = json.load(fh)[f"{curve_name}/{scheme}/{log_n}"]
+                    assert hashlib.sha256(gproof).hexdigest() == pinned
             finally:
                 cp.close()
         finally:

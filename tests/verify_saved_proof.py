@@ -43,7 +43,11 @@ def parse_vk(curve, scheme, vk):
 
 
 def verify_file(path, use_pairing=True):
-    d = json.load(open(path))
+    return verify_blob(json.load(open(path)), use_pairing)
+
+
+def verify_blob(d, use_pairing=True):
+    """d: {"curve", "pc", "max_degree", "beta", "gamma", "public_input": [str], "proof_hex", "vk_hex"} as written by bench.py"""
     curve, scheme = CURVES[d["curve"]], SCHEMES[d["pc"]]
     vk_bytes, proof_bytes = bytes.fromhex(d["vk_hex"]), bytes.fromhex(d["proof_hex"])
     (num_variables, num_constraints, num_non_zero), comms = parse_vk(curve, scheme, vk_bytes)
