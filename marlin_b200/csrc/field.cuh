@@ -23,7 +23,11 @@
 #define __device__
 #endif
 #ifndef __forceinline__
+#ifdef B2M_HOST_LIGHT_INLINE  // host test builds: let the compiler decide (the fully inlined form takes minutes to compile)
+#define __forceinline__ inline
+#else
 #define __forceinline__ inline __attribute__((always_inline))
+#endif
 #endif
 #endif
 

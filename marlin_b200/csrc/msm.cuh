@@ -65,8 +65,11 @@ struct Msm {
   size_t affine_min_refs = MSM_AFFINE_MIN_REFS;  // B2M_MSM_AFFINE_MIN_REFS
   int affine_map = 1;       // output -> thread mapping of the levels: 1 = warp-interleaved (coalesced), 0 = blocked; B2M_MSM_AFFINE_MAP
   int affine_scr = 0;       // level 0 gathers its operands once into a thread-contiguous scratch; B2M_MSM_AFFINE_SCR
+  int affine_U = 0;         // outputs per inversion (sub-batch of a thread's T outputs; 0 = T); B2M_MSM_AFFINE_U
+  int affine_classes = 0;   // phase classes: co-resident CTAs shorten their first sub-batch differently (msm_affine.cuh); B2M_MSM_AFFINE_CLASSES
   int affine_T = 64;        // additions per thread and inversion in those levels; B2M_MSM_AFFINE_T
   int acc_ctas_per_sm = 3;  // resident CTAs of msm_accumulate_kernel per SM (occupancy query)
+  DBuf<uint32_t> cls_ctr;   // [1024] per-SM CTA arrival counters for the phase classes
   DBuf<Affine<Fq>> tables;  // [W][stride]:  tables[w * stride + k] = 2^(c*w) * P_(k * world + rank)
 
   static int pick_window(size_t n);

@@ -55,6 +55,8 @@ struct AffLevel {
   // gathers both operands of every output ONCE from the window tables (sign applied) and parks them here, thread-
   // contiguous; pass 2 streams them back instead of gathering the same two random 96-byte points a second time.
   uint4* opnd;
+  uint32_t U;  // outputs per inversion: a thread's T outputs are processed in sub-batches of U (0: one batch of T)
+  uint32_t* cls_ctr;  // phase classes (null: off): per-SM arrival counters, a CTA's class = its arrival number on its SM mod 4
 };
 
 struct AffMap {
@@ -226,13 +228,22 @@ B2M_HD void aff_opnd_load(const uint4* opnd, size_t nth, uint32_t k, uint32_t t,
   }
 }
 
-// ---- arithmetic: thread t adds the planned pairs of its T outputs with one shared inversion -----------------------
+// ---- arithmetic: thread t adds the planned pairs of its T outputs, one shared inversion per sub-batch ----------------
 // PF = 1: load the next iteration's operands before the current iteration's multiplications in BOTH passes (costs ~50
 // registers, so fewer resident warps); PF = 2: in the denominator pass only (free: that pass is far below the register
 // high-water mark of the addition pass); PF = 0: loads are issued at use and latency is hidden by occupancy alone.
 // SCR (level 0): gather each operand once -- pass 1 loads the full points, parks them in A.opnd, pass 2 streams them.
+//
+// Sub-batches and phase classes.  Every thread does the same amount of work and every CTA of a wave starts at the same
+// time, so the warps that share an SM sub-partition march through the three phases in lock-step: all of them in the
+// memory-bound denominator pass (multiplier mostly idle), all of them in the ALU-only inversion (multiplier idle), all of
+// them in the multiplier-bound addition pass (3 of 4 waiting for the pipe) -- ncu showed the multiplier busy only ~60 %
+// of the time with every individual pipe far from saturated.  So a thread cuts its T outputs into sub-batches of A.U
+// outputs, each with its own prefix chain and inversion, and the FIRST sub-batch is shortened by the warp's phase class
+// (`cls` in 0..3, different for the CTAs that are co-resident on an SM): co-resident warps are then a quarter of a cycle
+// apart, and one warp's denominator pass / inversion runs under the other warps' multiplications.
 template <class Fq, int PF, bool SCR>
-B2M_HD void aff_level_thread(const AffLevel<Fq>& A, const Affine<Fq>* base, uint32_t t) {
+B2M_HD void aff_level_thread(const AffLevel<Fq>& A, const Affine<Fq>* base, uint32_t t, uint32_t cls = 3) {
   const uint32_t total = B2M_AFF_LDG32(A.off_out + A.B);
   const AffMap mp = aff_map(A, t, total);
   if (!mp.cnt) return;
@@ -240,160 +251,165 @@ B2M_HD void aff_level_thread(const AffLevel<Fq>& A, const Affine<Fq>* base, uint
   const size_t nth = A.nthreads;
   const uint4* meta = A.meta + t;
   Fq* pref = A.pref + t;
-  // ---- pass 1: denominators, running product ----------------------------------------------------
-  Fq run = Fq::one();
-  if (SCR) {
-    uint4 m = meta[0];
-    Affine<Fq> Pn, Qn;
-    if (PF) {
-      Pn = aff_ld(base, m.x);
-      Qn = aff_ld(base, m.y);
-    }
-    for (uint32_t k = 0; k < cnt; k++) {
-      const uint4 mc = m;
-      Affine<Fq> P, Q;
+  const uint32_t U = A.U ? A.U : A.T;
+  uint32_t first = (U * ((cls & 3u) + 1u)) / 4u;
+  if (first == 0) first = 1;
+  for (uint32_t kb = 0, ke = first < cnt ? first : cnt; kb < cnt; kb = ke, ke = (cnt - ke > U) ? ke + U : cnt) {
+    // ---- pass 1 over [kb, ke): denominators, running product ------------------------------------
+    Fq run = Fq::one();
+    if (SCR) {
+      uint4 m = meta[(size_t)kb * nth];
+      Affine<Fq> Pn, Qn;
       if (PF) {
-        P = Pn;
-        Q = Qn;
-      } else {
-        P = aff_ld(base, mc.x);
-        Q = aff_ld(base, mc.y);
+        Pn = aff_ld(base, m.x);
+        Qn = aff_ld(base, m.y);
       }
-      if (k + 1 < cnt) {
-        m = meta[(size_t)(k + 1) * nth];
+      for (uint32_t k = kb; k < ke; k++) {
+        const uint4 mc = m;
+        Affine<Fq> P, Q;
         if (PF) {
-          Pn = aff_ld(base, m.x);
-          Qn = aff_ld(base, m.y);
-        }
-      }
-      P = aff_signed(P, mc.x);
-      Q = aff_signed(Q, mc.y);
-      aff_opnd_store(A.opnd, nth, k, t, P, Q);
-      Fq den = Fq::one();
-      if (mc.w) {
-        Fq d;
-        const AffKind kind = aff_classify(P, Q, &d);
-        if (kind == AFF_ADD || kind == AFF_DBL) den = d;
-      }
-      run = k ? run * den : den;
-      B2M_AFF_ST(pref + (size_t)k * nth, run);
-    }
-  } else {
-    uint4 m = meta[0];
-    uint4 m1 = cnt > 1 ? meta[nth] : m;
-    Fq x1, x2;
-    if (PF) {
-      x1 = aff_ldx(base, m.x);
-      x2 = aff_ldx(base, m.y);
-    }
-    for (uint32_t k = 0; k < cnt; k++) {
-      const uint4 mc = m;
-      Fq c1, c2;
-      if (PF) {
-        c1 = x1;
-        c2 = x2;
-      } else {
-        c1 = aff_ldx(base, mc.x);
-        c2 = aff_ldx(base, mc.y);
-      }
-      if (k + 1 < cnt) {  // the plan runs two outputs ahead, (PF) the operands one
-        m = m1;
-        if (k + 2 < cnt) m1 = meta[(size_t)(k + 2) * nth];
-        if (PF) {
-          x1 = aff_ldx(base, m.x);
-          x2 = aff_ldx(base, m.y);
-        }
-      }
-      Fq den = Fq::one();
-      if (mc.w) {
-        if (c1.is_zero() || c2.is_zero() || c1 == c2) {  // rare: infinity, doubling or cancellation
-          Fq d;
-          const AffKind kind = aff_classify(aff_signed(aff_ld(base, mc.x), mc.x), aff_signed(aff_ld(base, mc.y), mc.y), &d);
-          if (kind == AFF_ADD || kind == AFF_DBL) den = d;
-        } else {
-          den = c2 - c1;
-        }
-      }
-      run = k ? run * den : den;
-      B2M_AFF_ST(pref + (size_t)k * nth, run);
-    }
-  }
-  // ---- one inversion per thread (the product of non-zero denominators is never zero) -----------------
-  Fq inv = run.inverse_fast();
-  // ---- pass 2: walk back, peel one denominator at a time ----------------------------------------------
-  {
-    constexpr bool PF2 = PF == 1 && !SCR;
-    uint4 m = meta[(size_t)(cnt - 1) * nth];
-    uint4 m1 = cnt > 1 ? meta[(size_t)(cnt - 2) * nth] : m;
-    Affine<Fq> Pn, Qn;
-    Fq pfn = run;  // product of the denominators before the output (read for k > 0 only)
-    if (PF2) {
-      Pn = aff_ld(base, m.x);
-      Qn = aff_ld(base, m.y);
-      if (cnt > 1) pfn = B2M_AFF_LD(pref + (size_t)(cnt - 2) * nth);
-    }
-    for (uint32_t k = cnt; k-- > 0;) {
-      const uint4 mc = m;
-      Affine<Fq> P, Q;
-      Fq pf = run;
-      if (PF2) {
-        P = Pn;
-        Q = Qn;
-        pf = pfn;
-      } else {
-        if (SCR) {
-          aff_opnd_load(A.opnd, nth, k, t, &P, &Q);
+          P = Pn;
+          Q = Qn;
         } else {
           P = aff_ld(base, mc.x);
           Q = aff_ld(base, mc.y);
         }
-        if (k > 0) pf = B2M_AFF_LD(pref + (size_t)(k - 1) * nth);
-      }
-      if (!SCR) {  // (the scratch holds the points with the sign applied)
+        if (k + 1 < ke) {
+          m = meta[(size_t)(k + 1) * nth];
+          if (PF) {
+            Pn = aff_ld(base, m.x);
+            Qn = aff_ld(base, m.y);
+          }
+        }
         P = aff_signed(P, mc.x);
         Q = aff_signed(Q, mc.y);
-      }
-      if (k > 0) {
-        m = m1;
-        if (k > 1) m1 = meta[(size_t)(k - 2) * nth];
-        if (PF2) {
-          Pn = aff_ld(base, m.x);
-          Qn = aff_ld(base, m.y);
-          if (k > 1) pfn = B2M_AFF_LD(pref + (size_t)(k - 2) * nth);
+        aff_opnd_store(A.opnd, nth, k, t, P, Q);
+        Fq den = Fq::one();
+        if (mc.w) {
+          Fq d;
+          const AffKind kind = aff_classify(P, Q, &d);
+          if (kind == AFF_ADD || kind == AFF_DBL) den = d;
         }
+        run = k > kb ? run * den : den;
+        B2M_AFF_ST(pref + (size_t)k * nth, run);
       }
-      Affine<Fq> R = P;
-      if (mc.w) {
-        Fq den;
-        const AffKind kind = aff_classify(P, Q, &den);
-        if (kind == AFF_COPY_Q) {
-          R = Q;
-        } else if (kind == AFF_INF) {
-          R = Affine<Fq>::inf();
-        } else if (kind != AFF_COPY_P) {
-          Fq dinv = inv;
-          if (k > 0) dinv = inv * pf;
-          inv = inv * den;
-          Fq lam;
-          if (kind == AFF_ADD) {
-            lam = (Q.y - P.y) * dinv;
-            R.x = lam.sqr() - P.x - Q.x;
-          } else {
-            const Fq xx = P.x.sqr();
-            lam = (xx.dbl() + xx) * dinv;
-            R.x = lam.sqr() - P.x.dbl();
+    } else {
+      uint4 m = meta[(size_t)kb * nth];
+      uint4 m1 = ke - kb > 1 ? meta[(size_t)(kb + 1) * nth] : m;
+      Fq x1, x2;
+      if (PF) {
+        x1 = aff_ldx(base, m.x);
+        x2 = aff_ldx(base, m.y);
+      }
+      for (uint32_t k = kb; k < ke; k++) {
+        const uint4 mc = m;
+        Fq c1, c2;
+        if (PF) {
+          c1 = x1;
+          c2 = x2;
+        } else {
+          c1 = aff_ldx(base, mc.x);
+          c2 = aff_ldx(base, mc.y);
+        }
+        if (k + 1 < ke) {  // the plan runs two outputs ahead, (PF) the operands one
+          m = m1;
+          if (k + 2 < ke) m1 = meta[(size_t)(k + 2) * nth];
+          if (PF) {
+            x1 = aff_ldx(base, m.x);
+            x2 = aff_ldx(base, m.y);
           }
-          R.y = lam * (P.x - R.x) - P.y;
         }
+        Fq den = Fq::one();
+        if (mc.w) {
+          if (c1.is_zero() || c2.is_zero() || c1 == c2) {  // rare: infinity, doubling or cancellation
+            Fq d;
+            const AffKind kind = aff_classify(aff_signed(aff_ld(base, mc.x), mc.x), aff_signed(aff_ld(base, mc.y), mc.y), &d);
+            if (kind == AFF_ADD || kind == AFF_DBL) den = d;
+          } else {
+            den = c2 - c1;
+          }
+        }
+        run = k > kb ? run * den : den;
+        B2M_AFF_ST(pref + (size_t)k * nth, run);
       }
-      const uint32_t o = mp.o0 + k * mp.step;
-      B2M_AFF_ST(&A.out[o].x, R.x);
-      B2M_AFF_ST(&A.out[o].y, R.y);
-      if (A.out_refs) {
-        uint2 r;
-        r.x = o;
-        r.y = mc.z;  // window 0: `out` is addressed directly
-        A.out_refs[o] = r;
+    }
+    // ---- one inversion per sub-batch (the product of non-zero denominators is never zero) ---------
+    Fq inv = run.inverse_fast();
+    // ---- pass 2 over [kb, ke): walk back, peel one denominator at a time ---------------------------
+    {
+      constexpr bool PF2 = PF == 1 && !SCR;
+      uint4 m = meta[(size_t)(ke - 1) * nth];
+      uint4 m1 = ke - kb > 1 ? meta[(size_t)(ke - 2) * nth] : m;
+      Affine<Fq> Pn, Qn;
+      Fq pfn = run;  // product of the denominators before the output (read for k > kb only)
+      if (PF2) {
+        Pn = aff_ld(base, m.x);
+        Qn = aff_ld(base, m.y);
+        if (ke - kb > 1) pfn = B2M_AFF_LD(pref + (size_t)(ke - 2) * nth);
+      }
+      for (uint32_t k = ke; k-- > kb;) {
+        const uint4 mc = m;
+        Affine<Fq> P, Q;
+        Fq pf = run;
+        if (PF2) {
+          P = Pn;
+          Q = Qn;
+          pf = pfn;
+        } else {
+          if (SCR) {
+            aff_opnd_load(A.opnd, nth, k, t, &P, &Q);
+          } else {
+            P = aff_ld(base, mc.x);
+            Q = aff_ld(base, mc.y);
+          }
+          if (k > kb) pf = B2M_AFF_LD(pref + (size_t)(k - 1) * nth);
+        }
+        if (!SCR) {  // (the scratch holds the points with the sign applied)
+          P = aff_signed(P, mc.x);
+          Q = aff_signed(Q, mc.y);
+        }
+        if (k > kb) {
+          m = m1;
+          if (k > kb + 1) m1 = meta[(size_t)(k - 2) * nth];
+          if (PF2) {
+            Pn = aff_ld(base, m.x);
+            Qn = aff_ld(base, m.y);
+            if (k > kb + 1) pfn = B2M_AFF_LD(pref + (size_t)(k - 2) * nth);
+          }
+        }
+        Affine<Fq> R = P;
+        if (mc.w) {
+          Fq den;
+          const AffKind kind = aff_classify(P, Q, &den);
+          if (kind == AFF_COPY_Q) {
+            R = Q;
+          } else if (kind == AFF_INF) {
+            R = Affine<Fq>::inf();
+          } else if (kind != AFF_COPY_P) {
+            Fq dinv = inv;
+            if (k > kb) dinv = inv * pf;
+            inv = inv * den;
+            Fq lam;
+            if (kind == AFF_ADD) {
+              lam = (Q.y - P.y) * dinv;
+              R.x = lam.sqr() - P.x - Q.x;
+            } else {
+              const Fq xx = P.x.sqr();
+              lam = (xx.dbl() + xx) * dinv;
+              R.x = lam.sqr() - P.x.dbl();
+            }
+            R.y = lam * (P.x - R.x) - P.y;
+          }
+        }
+        const uint32_t o = mp.o0 + k * mp.step;
+        B2M_AFF_ST(&A.out[o].x, R.x);
+        B2M_AFF_ST(&A.out[o].y, R.y);
+        if (A.out_refs) {
+          uint2 r;
+          r.x = o;
+          r.y = mc.z;  // window 0: `out` is addressed directly
+          A.out_refs[o] = r;
+        }
       }
     }
   }

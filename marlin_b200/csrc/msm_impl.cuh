@@ -201,7 +201,19 @@ __global__ void __launch_bounds__(256) msm_affine_plan_kernel(const AffLevel<Fq>
 template <class Fq, int MINB, int PF, bool SCR>
 __global__ void __launch_bounds__(128, MINB) msm_affine_level_kernel(const AffLevel<Fq> A, const Affine<Fq>* __restrict__ base) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < A.nthreads) aff_level_thread<Fq, PF, SCR>(A, base, t);
+  // phase class = arrival number of this CTA on its SM (mod 4): the CTAs resident together on an SM always differ
+  __shared__ uint32_t s_cls;
+  if (threadIdx.x == 0) {
+    uint32_t c = 3u;
+    if (A.cls_ctr) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      c = atomicAdd(A.cls_ctr + (smid & 1023u), 1u) & 3u;
+    }
+    s_cls = c;
+  }
+  __syncthreads();
+  if (t < A.nthreads) aff_level_thread<Fq, PF, SCR>(A, base, t, s_cls);
 }
 
 // opt-in two-chain variant (msm_affine.cuh aff_level_thread_ilp): B2M_MSM_AFFINE_CTAS / B2M_MSM_AFFINE_CTAS_UPPER = 6
@@ -477,6 +489,12 @@ Msm<Fr, Fq>::Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, const Affine<
   if (const char* e = getenv("B2M_MSM_AFFINE_MIN_REFS")) affine_min_refs = (size_t)atoll(e);
   if (const char* e = getenv("B2M_MSM_AFFINE_MAP")) affine_map = atoi(e);
   if (const char* e = getenv("B2M_MSM_AFFINE_SCR")) affine_scr = atoi(e);
+  if (const char* e = getenv("B2M_MSM_AFFINE_U")) affine_U = atoi(e);
+  if (const char* e = getenv("B2M_MSM_AFFINE_CLASSES")) affine_classes = atoi(e);
+  if (affine_U < 0) affine_U = 0;
+  cls_ctr = DBuf<uint32_t>(cx, 1024);  // per-SM arrival counters of the level kernels (never reset: only the low bits matter)
+  cls_ctr.zero();
+  cx.sync();
   if (affine_levels < 0) affine_levels = 0;
   if (affine_levels > MSM_MAX_AFFINE_LEVELS) affine_levels = MSM_MAX_AFFINE_LEVELS;
   if (affine_T < 1) affine_T = 1;
@@ -656,7 +674,7 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
           const bool scr = l == 0 && affine_scr;
           AffLevel<Fq> A{tables.p, stride, sorted[s].p, l > 0 ? lvl_pts[(l - 1) & 1].p : nullptr, off_in, off_out, B, lvl_pts[l & 1].p,
                          l == LV - 1 ? lvl_refs.p : nullptr, lvl_pref.p, lvl_meta.p, (uint32_t)affine_T, nthreads, lane_step,
-                         scr ? lvl_opnd.p : nullptr};
+                         scr ? lvl_opnd.p : nullptr, (uint32_t)affine_U, affine_classes ? cls_ctr.p : nullptr};
           if (l == 0)
             msm_affine_plan_kernel<Fq, true><<<div_up(nthreads, 256), 256, 0, cx.stream>>>(A);
           else

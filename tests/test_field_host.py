@@ -19,7 +19,7 @@ def hostlib():
     src = os.path.join(HERE, "host", "field_host_shim.cpp")
     deps = [src] + [os.path.join(HERE, "..", "marlin_b200", "csrc", h) for h in ("field.cuh", "curve.cuh", "msm_affine.cuh")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", src, "-o", SO])
+        subprocess.check_call(["g++", "-O1", "-DB2M_HOST_LIGHT_INLINE", "-shared", "-fPIC", "-x", "c++", src, "-o", SO])
     return ctypes.CDLL(SO)
 
 
@@ -152,13 +152,17 @@ def test_batched_affine_levels(hostlib, ci, curve):
                  (1, 1, 0, 1, 0), (1, 4, 0, 1, 0), (2, 3, 0, 1, 0), (3, 2, 0, 1, 0), (4, 1, 2, 1, 0), (3, 8, 2, 1, 0), (7, 5, 0, 1, 0),
                  (2, 3, 1, 1, 0), (3, 2, 1, 1, 0), (4, 5, 1, 1, 0), (3, 64, 1, 1, 0),
                  (1, 1, 0, 1, 1), (2, 2, 0, 1, 1), (3, 3, 0, 1, 1), (3, 4, 2, 0, 1), (4, 1, 1, 1, 1), (3, 8, 0, 0, 1)]
-        for levels, T, variant, interleaved, scr in cases:
+        cases = [c + (0,) for c in cases]
+        # sub-batches of U outputs per inversion with per-thread phase classes (first sub-batch shortened)
+        cases += [(3, 8, 0, 1, 0, 4), (3, 8, 0, 1, 1, 3), (2, 7, 2, 1, 0, 2), (3, 64, 0, 1, 0, 32), (3, 64, 0, 1, 1, 16), (4, 5, 0, 0, 0, 1),
+                  (3, 9, 1, 1, 0, 4), (2, 6, 0, 0, 1, 8)]
+        for levels, T, variant, interleaved, scr, U in cases:
             out = np.zeros(B * 2 * n32, dtype=np.uint32)
             hostlib.affine_levels_host(ci, tab_l.ctypes.data_as(ctypes.c_void_p), refs_a.ctypes.data_as(ctypes.c_void_p),
                                        off_a.ctypes.data_as(ctypes.c_void_p), B, levels, T, out.ctypes.data_as(ctypes.c_void_p), variant,
-                                       interleaved, scr)
+                                       interleaved, scr, U)
             for b in range(B):
                 x = sum(int(out[b * 2 * n32 + i]) << (32 * i) for i in range(n32))
                 y = sum(int(out[b * 2 * n32 + n32 + i]) << (32 * i) for i in range(n32))
                 got = None if x == 0 and y == 0 else (fq.from_mont(x), fq.from_mont(y))
-                assert got == want[b], (trial, levels, T, variant, interleaved, scr, b)
+                assert got == want[b], (trial, levels, T, variant, interleaved, scr, U, b)
