@@ -526,4 +526,112 @@ B2M_HD void aff_level_thread_ilp(const AffLevel<Fq>& A, const Affine<Fq>* base, 
   }
 }
 
+// ---- software-pipelined variant (kernel variants 8 / 9) ---------------------------------------------------------------
+// What the captures of the variants above say (profiles/r02_level_kernel_notes.md): no pipe is saturated -- every warp simply
+// runs at its own latency-bound pace (a serial chain of five multiplications per output, each multiplication two carry
+// chains, operand loads issued at their point of use), and extra work of ANY kind (more inversions, more loads) adds its full
+// time.  This variant restructures the per-thread code instead of relying on co-resident warps:
+//  * branch-free fast path: den = fast ? x2 - x1 : 1 with fast = "a plain addition of two finite points with different x"
+//    (the same predicate in both passes); everything else -- copies of an unpaired point, P + (-P), doublings, operands at
+//    infinity -- takes its denominator out of the shared chain (den = 1) and is recomputed on its own in a cold fix-up,
+//    so each loop body is ONE basic block the scheduler can interleave freely;
+//  * the addition pass is software-pipelined over the outputs: iteration k peels the denominator of output k
+//    (dinv_k = inv * pref_k, inv *= den_k: two independent multiplications) while it finishes output k + 1
+//    (lambda, lambda^2, y3: a chain of three) -- two independent instruction streams per warp, and the operands of output
+//    k are requested one full iteration before their y coordinates are needed;
+//  * exclusive prefix products (pref_k = den_0 ... den_(k-1)), so no first-element special case.
+template <class Fq>
+B2M_HD bool aff_fast(uint32_t w, const Fq& x1, const Fq& x2) {
+  return w != 0 && !x1.is_zero() && !x2.is_zero() && !(x1 == x2);
+}
+// P + Q for the outputs outside the fast path (own inversion; rare or cheap)
+template <class Fq>
+B2M_HD Affine<Fq> aff_add_slow(const Affine<Fq>& P, const Affine<Fq>& Q, uint32_t w) {
+  if (!w) return P;
+  Fq den;
+  const AffKind kind = aff_classify(P, Q, &den);
+  if (kind == AFF_COPY_P) return P;
+  if (kind == AFF_COPY_Q) return Q;
+  if (kind == AFF_INF) return Affine<Fq>::inf();
+  Fq dummy;
+  return aff_finish(P, Q, true, den.inverse_fast(), &dummy);
+}
+
+template <class Fq>
+B2M_HD void aff_level_thread_sp(const AffLevel<Fq>& A, const Affine<Fq>* base, uint32_t t) {
+  const uint32_t total = B2M_AFF_LDG32(A.off_out + A.B);
+  const AffMap mp = aff_map(A, t, total);
+  if (!mp.cnt) return;
+  const uint32_t cnt = mp.cnt;
+  const size_t nth = A.nthreads;
+  const uint4* meta = A.meta + t;
+  Fq* pref = A.pref + t;
+  // ---- pass 1: exclusive prefix products of the denominators; operands one output ahead ---------------------------
+  Fq run = Fq::one();
+  {
+    uint4 m = meta[0];
+    Fq x1 = aff_ldx(base, m.x), x2 = aff_ldx(base, m.y);
+    for (uint32_t k = 0; k < cnt; k++) {
+      const uint4 mc = m;
+      const Fq c1 = x1, c2 = x2;
+      if (k + 1 < cnt) {
+        m = meta[(size_t)(k + 1) * nth];
+        x1 = aff_ldx(base, m.x);
+        x2 = aff_ldx(base, m.y);
+      }
+      const Fq d = c2 - c1;
+      const Fq den = aff_fast(mc.w, c1, c2) ? d : Fq::one();
+      B2M_AFF_ST(pref + (size_t)k * nth, run);
+      run = run * den;
+    }
+  }
+  Fq inv = run.inverse_fast();
+  // ---- pass 2, software-pipelined -----------------------------------------------------------------------------------
+  // current = the output whose denominator has been peeled (dinv_c known) and whose sum is still to be formed
+  uint4 m_c = meta[(size_t)(cnt - 1) * nth];
+  Affine<Fq> P_c = aff_signed(aff_ld(base, m_c.x), m_c.x), Q_c = aff_signed(aff_ld(base, m_c.y), m_c.y);
+  bool fast_c = aff_fast(m_c.w, P_c.x, Q_c.x);
+  Fq dinv_c;
+  {
+    const Fq pf = B2M_AFF_LD(pref + (size_t)(cnt - 1) * nth);
+    const Fq d = Q_c.x - P_c.x;
+    const Fq den = fast_c ? d : Fq::one();
+    dinv_c = inv * pf;
+    inv = inv * den;
+  }
+  for (uint32_t k = cnt - 1; k-- > 0;) {
+    // request output k's operands; finish output k + 1 meanwhile
+    const uint4 m_n = meta[(size_t)k * nth];
+    const Affine<Fq> P_r = aff_ld(base, m_n.x), Q_r = aff_ld(base, m_n.y);
+    const Fq pf = B2M_AFF_LD(pref + (size_t)k * nth);
+    // stage B (output k + 1): lambda, x3, y3 -- computed unconditionally, replaced below when the output is not a fast one
+    const Fq lam = (Q_c.y - P_c.y) * dinv_c;
+    Affine<Fq> R;
+    R.x = lam.sqr() - P_c.x - Q_c.x;
+    R.y = lam * (P_c.x - R.x) - P_c.y;
+    // stage A (output k): peel its denominator
+    const Affine<Fq> P_n = aff_signed(P_r, m_n.x), Q_n = aff_signed(Q_r, m_n.y);
+    const bool fast_n = aff_fast(m_n.w, P_n.x, Q_n.x);
+    const Fq d = Q_n.x - P_n.x;
+    const Fq den = fast_n ? d : Fq::one();
+    const Fq dinv_n = inv * pf;
+    inv = inv * den;
+    if (!fast_c) R = aff_add_slow(P_c, Q_c, m_c.w);  // cold
+    aff_store_out(A, mp.o0 + (k + 1) * mp.step, R, m_c.z);
+    m_c = m_n;
+    P_c = P_n;
+    Q_c = Q_n;
+    fast_c = fast_n;
+    dinv_c = dinv_n;
+  }
+  {  // epilogue: output 0
+    const Fq lam = (Q_c.y - P_c.y) * dinv_c;
+    Affine<Fq> R;
+    R.x = lam.sqr() - P_c.x - Q_c.x;
+    R.y = lam * (P_c.x - R.x) - P_c.y;
+    if (!fast_c) R = aff_add_slow(P_c, Q_c, m_c.w);
+    aff_store_out(A, mp.o0, R, m_c.z);
+  }
+}
+
 }  // namespace b2m

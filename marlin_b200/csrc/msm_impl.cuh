@@ -216,6 +216,13 @@ __global__ void __launch_bounds__(128, MINB) msm_affine_level_kernel(const AffLe
   if (t < A.nthreads) aff_level_thread<Fq, PF, SCR>(A, base, t, s_cls);
 }
 
+// software-pipelined variant (msm_affine.cuh aff_level_thread_sp): variants 8 (3 CTAs/SM), 9 (2), 10 (4)
+template <class Fq, int MINB>
+__global__ void __launch_bounds__(128, MINB) msm_affine_level_sp_kernel(const AffLevel<Fq> A, const Affine<Fq>* __restrict__ base) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < A.nthreads) aff_level_thread_sp<Fq>(A, base, t);
+}
+
 // opt-in two-chain variant (msm_affine.cuh aff_level_thread_ilp): B2M_MSM_AFFINE_CTAS / B2M_MSM_AFFINE_CTAS_UPPER = 6
 template <class Fq>
 __global__ void __launch_bounds__(128, 2) msm_affine_level_ilp_kernel(const AffLevel<Fq> A, const Affine<Fq>* __restrict__ base) {
@@ -693,6 +700,9 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
           } else {
             switch (variant) {
               case 6: msm_affine_level_ilp_kernel<Fq><<<grid, 128, 0, cx.stream>>>(A, base); break;
+              case 8: msm_affine_level_sp_kernel<Fq, 3><<<grid, 128, 0, cx.stream>>>(A, base); break;
+              case 9: msm_affine_level_sp_kernel<Fq, 2><<<grid, 128, 0, cx.stream>>>(A, base); break;
+              case 10: msm_affine_level_sp_kernel<Fq, 4><<<grid, 128, 0, cx.stream>>>(A, base); break;
               case 3: msm_affine_level_kernel<Fq, 3, 1, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
               case 5: msm_affine_level_kernel<Fq, 5, 0, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
               case 7: msm_affine_level_kernel<Fq, 4, 2, false><<<grid, 128, 0, cx.stream>>>(A, base); break;

@@ -86,6 +86,7 @@ static void run_levels(const uint32_t* tables, const uint32_t* refs, const uint3
       if (use_scr) {
         if (T & 1) aff_level_thread<Fq, 2, true>(A, base, t, cls); else aff_level_thread<Fq, 0, true>(A, base, t, cls);
       } else if (variant == 1) aff_level_thread_ilp<Fq>(A, base, t);
+      else if (variant == 3) aff_level_thread_sp<Fq>(A, base, t);
       else if (variant == 2) aff_level_thread<Fq, 2, false>(A, base, t, cls);
       else if (T & 1) aff_level_thread<Fq, 1, false>(A, base, t, cls);
       else aff_level_thread<Fq, 0, false>(A, base, t, cls);
