@@ -56,6 +56,7 @@ struct AffLevel {
   // contiguous; pass 2 streams them back instead of gathering the same two random 96-byte points a second time.
   uint4* opnd;
   uint32_t U;  // outputs per inversion: a thread's T outputs are processed in sub-batches of U (0: one batch of T)
+  Fq* inv;            // [nthreads] chain inverses (split kernels: written by phase 1, read by phase 2)
   uint32_t* cls_ctr;  // phase classes (null: off): per-SM arrival counters, a CTA's class = its arrival number on its SM mod 4
 };
 
@@ -557,7 +558,16 @@ B2M_HD Affine<Fq> aff_add_slow(const Affine<Fq>& P, const Affine<Fq>& Q, uint32_
   return aff_finish(P, Q, true, den.inverse_fast(), &dummy);
 }
 
-template <class Fq>
+// PHASE 0: both passes in one call.  PHASE 1 / 2: the split form -- two kernels per level.  What limits the fused kernel
+// (profiles/r02_level_kernel_notes.md): a single warp can issue an IMAD.WIDE only every ~6.5 cycles (the carry chains),
+// i.e. drive the multiplier to ~62 %, so the pipe is full only while >= 2 warps of a sub-partition are inside
+// multiplication code at the same time; the fused kernel's warps spend 40-60 % of their time elsewhere (operand
+// latency of the denominator pass, the ALU-only inversion) at 2-4 resident warps per sub-partition.  Split:
+//   PHASE 1 = denominator pass + inversion: ~90 registers, 5-6 CTAs/SM -- the gathers' latency and the inversions'
+//             ~27 k ALU instructions are spread over 5-6 warps per sub-partition instead of blocking a 128-168-register warp;
+//   PHASE 2 = addition pass only: every resident warp is inside multiplication code nearly all the time.
+// The chain inverse crosses in A.inv[t].
+template <class Fq, int PHASE, bool PIPE = true>
 B2M_HD void aff_level_thread_sp(const AffLevel<Fq>& A, const Affine<Fq>* base, uint32_t t) {
   const uint32_t total = B2M_AFF_LDG32(A.off_out + A.B);
   const AffMap mp = aff_map(A, t, total);
@@ -566,26 +576,57 @@ B2M_HD void aff_level_thread_sp(const AffLevel<Fq>& A, const Affine<Fq>* base, u
   const size_t nth = A.nthreads;
   const uint4* meta = A.meta + t;
   Fq* pref = A.pref + t;
-  // ---- pass 1: exclusive prefix products of the denominators; operands one output ahead ---------------------------
-  Fq run = Fq::one();
-  {
+  Fq inv;
+  if (PHASE != 2) {
+    // ---- pass 1: exclusive prefix products of the denominators; the plan two outputs ahead, the operands one ---------
+    Fq run = Fq::one();
     uint4 m = meta[0];
+    uint4 m1 = cnt > 1 ? meta[nth] : m;
     Fq x1 = aff_ldx(base, m.x), x2 = aff_ldx(base, m.y);
     for (uint32_t k = 0; k < cnt; k++) {
-      const uint4 mc = m;
+      const uint32_t w = m.w;
       const Fq c1 = x1, c2 = x2;
       if (k + 1 < cnt) {
-        m = meta[(size_t)(k + 1) * nth];
+        m = m1;
+        if (k + 2 < cnt) m1 = meta[(size_t)(k + 2) * nth];
         x1 = aff_ldx(base, m.x);
         x2 = aff_ldx(base, m.y);
       }
       const Fq d = c2 - c1;
-      const Fq den = aff_fast(mc.w, c1, c2) ? d : Fq::one();
+      const Fq den = aff_fast(w, c1, c2) ? d : Fq::one();
       B2M_AFF_ST(pref + (size_t)k * nth, run);
       run = run * den;
     }
+    inv = run.inverse_fast();
+    if (PHASE == 1) {
+      B2M_AFF_ST(A.inv + t, inv);
+      return;
+    }
+  } else {
+    inv = B2M_AFF_LD(A.inv + t);
   }
-  Fq inv = run.inverse_fast();
+  if (!PIPE) {
+    // ---- pass 2, plain form (fewer live registers: more resident warps): one output per iteration -----------------------
+    uint4 m = meta[(size_t)(cnt - 1) * nth];
+    for (uint32_t k = cnt; k-- > 0;) {
+      const uint4 mc = m;
+      const Affine<Fq> P = aff_signed(aff_ld(base, mc.x), mc.x), Q = aff_signed(aff_ld(base, mc.y), mc.y);
+      const Fq pf = B2M_AFF_LD(pref + (size_t)k * nth);
+      if (k > 0) m = meta[(size_t)(k - 1) * nth];
+      const bool fast = aff_fast(mc.w, P.x, Q.x);
+      const Fq d = Q.x - P.x;
+      const Fq den = fast ? d : Fq::one();
+      const Fq dinv = inv * pf;
+      inv = inv * den;
+      const Fq lam = (Q.y - P.y) * dinv;
+      Affine<Fq> R;
+      R.x = lam.sqr() - P.x - Q.x;
+      R.y = lam * (P.x - R.x) - P.y;
+      if (!fast) R = aff_add_slow(P, Q, mc.w);  // cold
+      aff_store_out(A, mp.o0 + k * mp.step, R, mc.z);
+    }
+    return;
+  }
   // ---- pass 2, software-pipelined -----------------------------------------------------------------------------------
   // current = the output whose denominator has been peeled (dinv_c known) and whose sum is still to be formed
   uint4 m_c = meta[(size_t)(cnt - 1) * nth];

@@ -217,10 +217,10 @@ __global__ void __launch_bounds__(128, MINB) msm_affine_level_kernel(const AffLe
 }
 
 // software-pipelined variant (msm_affine.cuh aff_level_thread_sp): variants 8 (3 CTAs/SM), 9 (2), 10 (4)
-template <class Fq, int MINB>
+template <class Fq, int MINB, int PHASE, bool PIPE = true>
 __global__ void __launch_bounds__(128, MINB) msm_affine_level_sp_kernel(const AffLevel<Fq> A, const Affine<Fq>* __restrict__ base) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < A.nthreads) aff_level_thread_sp<Fq>(A, base, t);
+  if (t < A.nthreads) aff_level_thread_sp<Fq, PHASE, PIPE>(A, base, t);
 }
 
 // opt-in two-chain variant (msm_affine.cuh aff_level_thread_ilp): B2M_MSM_AFFINE_CTAS / B2M_MSM_AFFINE_CTAS_UPPER = 6
@@ -613,7 +613,7 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
     DBuf<uint32_t> lvl_off[2], lvl_cnt;
     DBuf<uint2> lvl_refs;
     DBuf<uint4> lvl_meta, lvl_opnd;
-    DBuf<Fq> lvl_pref;
+    DBuf<Fq> lvl_pref, lvl_inv;
     if (LV > 0) {
       lvl_pts[0] = DBuf<Affine<Fq>>(cx, bound[1]);
       if (LV > 1) lvl_pts[1] = DBuf<Affine<Fq>>(cx, bound[2]);
@@ -622,6 +622,7 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       const size_t slots_l0 = (size_t)affine_T * ((bound[1] + affine_T - 1) / affine_T + 128);  // >= T * nthreads for either mapping
       lvl_meta = DBuf<uint4>(cx, slots_l0);
       lvl_pref = DBuf<Fq>(cx, slots_l0);
+      lvl_inv = DBuf<Fq>(cx, slots_l0 / affine_T + 1);
       if (affine_scr) lvl_opnd = DBuf<uint4>(cx, slots_l0 * (2 * sizeof(Affine<Fq>) / 16));
     }
     buckets.zero();  // empty buckets are never written: all-zero XYZZ is the point at infinity
@@ -681,7 +682,7 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
           const bool scr = l == 0 && affine_scr;
           AffLevel<Fq> A{tables.p, stride, sorted[s].p, l > 0 ? lvl_pts[(l - 1) & 1].p : nullptr, off_in, off_out, B, lvl_pts[l & 1].p,
                          l == LV - 1 ? lvl_refs.p : nullptr, lvl_pref.p, lvl_meta.p, (uint32_t)affine_T, nthreads, lane_step,
-                         scr ? lvl_opnd.p : nullptr, (uint32_t)affine_U, affine_classes ? cls_ctr.p : nullptr};
+                         scr ? lvl_opnd.p : nullptr, (uint32_t)affine_U, lvl_inv.p, affine_classes ? cls_ctr.p : nullptr};
           if (l == 0)
             msm_affine_plan_kernel<Fq, true><<<div_up(nthreads, 256), 256, 0, cx.stream>>>(A);
           else
@@ -700,9 +701,19 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
           } else {
             switch (variant) {
               case 6: msm_affine_level_ilp_kernel<Fq><<<grid, 128, 0, cx.stream>>>(A, base); break;
-              case 8: msm_affine_level_sp_kernel<Fq, 3><<<grid, 128, 0, cx.stream>>>(A, base); break;
-              case 9: msm_affine_level_sp_kernel<Fq, 2><<<grid, 128, 0, cx.stream>>>(A, base); break;
-              case 10: msm_affine_level_sp_kernel<Fq, 4><<<grid, 128, 0, cx.stream>>>(A, base); break;
+              case 8: msm_affine_level_sp_kernel<Fq, 3, 0><<<grid, 128, 0, cx.stream>>>(A, base); break;
+              case 9: msm_affine_level_sp_kernel<Fq, 2, 0><<<grid, 128, 0, cx.stream>>>(A, base); break;
+              // split form: denominator pass + inversion at high occupancy, then the addition pass on its own
+              case 11: case 12: case 13: case 14: case 15: case 16: {
+                if (variant <= 13) msm_affine_level_sp_kernel<Fq, 5, 1><<<grid, 128, 0, cx.stream>>>(A, base);
+                else msm_affine_level_sp_kernel<Fq, 6, 1><<<grid, 128, 0, cx.stream>>>(A, base);
+                const int v2 = (variant - 11) % 3;
+                if (v2 == 0) msm_affine_level_sp_kernel<Fq, 3, 2><<<grid, 128, 0, cx.stream>>>(A, base);
+                else if (v2 == 1) msm_affine_level_sp_kernel<Fq, 2, 2><<<grid, 128, 0, cx.stream>>>(A, base);
+                else msm_affine_level_sp_kernel<Fq, 4, 2, false><<<grid, 128, 0, cx.stream>>>(A, base);
+                cx.launches++;
+                break;
+              }
               case 3: msm_affine_level_kernel<Fq, 3, 1, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
               case 5: msm_affine_level_kernel<Fq, 5, 0, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
               case 7: msm_affine_level_kernel<Fq, 4, 2, false><<<grid, 128, 0, cx.stream>>>(A, base); break;

@@ -73,10 +73,11 @@ static void run_levels(const uint32_t* tables, const uint32_t* refs, const uint3
     out_refs.assign(total, uint2{0, 0});
     std::vector<Fq> pref((size_t)T * (nthreads ? nthreads : 1));
     std::vector<uint4> meta((size_t)T * (nthreads ? nthreads : 1));
+    std::vector<Fq> invs(nthreads ? nthreads : 1);
     const bool use_scr = scr && l == 0;
     std::vector<uint4> opnd(use_scr ? (size_t)T * (nthreads ? nthreads : 1) * (2 * sizeof(Affine<Fq>) / 16) : 1);
     AffLevel<Fq> A{tab, 0, sorted, in.data(), off_in.data(), off_out.data(), B, out.data(), l == levels - 1 ? out_refs.data() : nullptr,
-                   pref.data(), meta.data(), T, nthreads, lane_step, use_scr ? opnd.data() : nullptr, U, nullptr};
+                   pref.data(), meta.data(), T, nthreads, lane_step, use_scr ? opnd.data() : nullptr, U, invs.data(), nullptr};
     for (uint32_t t = 0; t < nthreads; t++) {
       if (l == 0) aff_plan_thread<Fq, true>(A, t); else aff_plan_thread<Fq, false>(A, t);
     }
@@ -86,7 +87,9 @@ static void run_levels(const uint32_t* tables, const uint32_t* refs, const uint3
       if (use_scr) {
         if (T & 1) aff_level_thread<Fq, 2, true>(A, base, t, cls); else aff_level_thread<Fq, 0, true>(A, base, t, cls);
       } else if (variant == 1) aff_level_thread_ilp<Fq>(A, base, t);
-      else if (variant == 3) aff_level_thread_sp<Fq>(A, base, t);
+      else if (variant == 3) aff_level_thread_sp<Fq, 0>(A, base, t);
+      else if (variant == 4) { aff_level_thread_sp<Fq, 1>(A, base, t); aff_level_thread_sp<Fq, 2>(A, base, t); }
+      else if (variant == 5) { aff_level_thread_sp<Fq, 1>(A, base, t); aff_level_thread_sp<Fq, 2, false>(A, base, t); }
       else if (variant == 2) aff_level_thread<Fq, 2, false>(A, base, t, cls);
       else if (T & 1) aff_level_thread<Fq, 1, false>(A, base, t, cls);
       else aff_level_thread<Fq, 0, false>(A, base, t, cls);

@@ -154,7 +154,9 @@ def test_batched_affine_levels(hostlib, ci, curve):
                  (1, 1, 0, 1, 1), (2, 2, 0, 1, 1), (3, 3, 0, 1, 1), (3, 4, 2, 0, 1), (4, 1, 1, 1, 1), (3, 8, 0, 0, 1)]
         cases = [c + (0,) for c in cases]
         # variant 3: the software-pipelined thread function
-        cases += [(1, 1, 3, 1, 0, 0), (1, 2, 3, 1, 0, 0), (2, 3, 3, 1, 0, 0), (3, 8, 3, 1, 0, 0), (4, 5, 3, 0, 0, 0), (7, 4, 3, 1, 0, 0), (3, 64, 3, 1, 0, 0)]
+        cases += [(1, 1, 5, 1, 0, 0), (2, 3, 5, 1, 0, 0), (3, 8, 5, 0, 0, 0), (3, 64, 5, 1, 0, 0),  # 5: split, plain addition pass
+                  (1, 1, 4, 1, 0, 0), (2, 3, 4, 1, 0, 0), (3, 8, 4, 0, 0, 0), (3, 64, 4, 1, 0, 0),  # 4: its split (two-kernel) form
+                  (1, 1, 3, 1, 0, 0), (1, 2, 3, 1, 0, 0), (2, 3, 3, 1, 0, 0), (3, 8, 3, 1, 0, 0), (4, 5, 3, 0, 0, 0), (7, 4, 3, 1, 0, 0), (3, 64, 3, 1, 0, 0)]
         # sub-batches of U outputs per inversion with per-thread phase classes (first sub-batch shortened)
         cases += [(3, 8, 0, 1, 0, 4), (3, 8, 0, 1, 1, 3), (2, 7, 2, 1, 0, 2), (3, 64, 0, 1, 0, 32), (3, 64, 0, 1, 1, 16), (4, 5, 0, 0, 0, 1),
                   (3, 9, 1, 1, 0, 4), (2, 6, 0, 0, 1, 8)]

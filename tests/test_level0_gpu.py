@@ -194,7 +194,8 @@ def test_msm_skewed_scalars(b2m_ctx):
     (3, 4, 6, 6, 1, 0), (2, 7, 6, 4, 1, 0), (3, 64, 4, 6, 1, 0), (3, 5, 7, 7, 1, 0),                      # two-chain (ILP), pass-1 prefetch
     (3, 64, 4, 4, 1, 1), (2, 3, 7, 4, 1, 1), (4, 1, 4, 6, 1, 1),                                           # level 0 through the operand scratch
     (3, 64, 4, 4, 0, 0), (2, 5, 6, 6, 0, 0), (3, 3, 3, 7, 0, 1)]] + [                                      # blocked mapping
-    (3, 64, 8, 8, 1, 0, 0), (2, 3, 9, 10, 1, 0, 0), (4, 1, 10, 8, 0, 0, 0), (1, 7, 8, 8, 1, 0, 0),  # software-pipelined kernels
+    (3, 64, 8, 8, 1, 0, 0), (2, 3, 9, 9, 1, 0, 0), (4, 1, 9, 8, 0, 0, 0), (1, 7, 8, 8, 1, 0, 0),  # software-pipelined kernels
+    (3, 64, 11, 13, 1, 0, 0), (2, 3, 12, 14, 1, 0, 0), (4, 1, 15, 16, 0, 0, 0), (3, 5, 13, 11, 1, 0, 0), (1, 64, 16, 16, 1, 0, 0),  # split: two kernels per level
     (3, 64, 4, 4, 1, 0, 32), (3, 64, 4, 4, 1, 1, 16), (2, 8, 7, 3, 1, 0, 3), (4, 128, 4, 4, 1, 0, 48), (3, 5, 4, 4, 0, 0, 2)])  # sub-batches + phase classes
 def test_msm_affine_levels_forced(b2m_ctx, monkeypatch, levels, T, variant, upper, mapping, scr, sub):
     """The batched-affine levels (csrc/msm_affine.cuh) are skipped for small MSMs; force them on (any size, odd
