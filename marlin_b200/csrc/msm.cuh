@@ -60,16 +60,12 @@ struct Msm {
   // Off for a 254-bit Fq: its multiplications are so cheap that the levels' extra memory traffic costs more
   // than the saved multiplications (BN254 2^20: 126.6 ms with, 120.6 ms without).
   int affine_levels = Fq::N > 8 ? 3 : 0;
-  int affine_ctas_upper = 4;  // the same for levels >= 1 (streaming operands); B2M_MSM_AFFINE_CTAS_UPPER, 6 = two-chain ILP variant
-  int affine_ctas = 4;      // level-kernel variant: resident CTAs per SM it is compiled for (B2M_MSM_AFFINE_CTAS: 3 = with prefetch, 4, 5)
+  int affine_ctas_upper = 4;  // the same for levels >= 1 (streaming operands); B2M_MSM_AFFINE_CTAS_UPPER
+  int affine_ctas = 4;      // level-kernel variant of level 0 (B2M_MSM_AFFINE_CTAS; the list is at the launch site in msm_impl.cuh)
   size_t affine_min_refs = MSM_AFFINE_MIN_REFS;  // B2M_MSM_AFFINE_MIN_REFS
   int affine_map = 1;       // output -> thread mapping of the levels: 1 = warp-interleaved (coalesced), 0 = blocked; B2M_MSM_AFFINE_MAP
-  int affine_scr = 0;       // level 0 gathers its operands once into a thread-contiguous scratch; B2M_MSM_AFFINE_SCR
-  int affine_U = 0;         // outputs per inversion (sub-batch of a thread's T outputs; 0 = T); B2M_MSM_AFFINE_U
-  int affine_classes = 0;   // phase classes: co-resident CTAs shorten their first sub-batch differently (msm_affine.cuh); B2M_MSM_AFFINE_CLASSES
   int affine_T = 64;        // additions per thread and inversion in those levels; B2M_MSM_AFFINE_T
   int acc_ctas_per_sm = 3;  // resident CTAs of msm_accumulate_kernel per SM (occupancy query)
-  DBuf<uint32_t> cls_ctr;   // [1024] per-SM CTA arrival counters for the phase classes
   DBuf<Affine<Fq>> tables;  // [W][stride]:  tables[w * stride + k] = 2^(c*w) * P_(k * world + rank)
 
   static int pick_window(size_t n);

@@ -6,9 +6,12 @@
 // = point 2j + point 2j + 1 (or a copy of point 2j when the count is odd).  All additions of a level are
 // independent, so they are done in AFFINE coordinates with the slopes' denominators inverted together
 // (Montgomery's trick): 6 field multiplications per addition instead of 10 for an XYZZ mixed addition.
-// A light plan pass resolves which two points make each output.  A thread then owns T consecutive outputs: pass 1 multiplies the denominators up (prefix products to a scratch
-// array), one binary-Euclid inversion (field.cuh inverse_fast: adds and shifts only, it runs on the ALU pipe
-// while other warps multiply), pass 2 walks back and writes the sums.  After a few levels the remaining points
+// A light plan pass resolves which two points make each output.  A thread then owns T outputs (warp-interleaved: the 32
+// lanes of a warp own 32 T consecutive outputs, so every step of a warp touches 32 adjacent outputs): pass 1 multiplies
+// the denominators up (prefix products to a scratch array), one binary-Euclid inversion (field.cuh inverse_fast: adds and
+// shifts only), pass 2 walks back and writes the sums.  Three forms of the arithmetic kernel are kept, all byte-identical
+// in their results (profiles/r02_level_kernel_notes.md has the measurements that chose the default): the fused kernel
+// (aff_level_thread), a branch-free software-pipelined one (aff_level_thread_sp) and the latter's split into two kernels.  After a few levels the remaining points
 // (n / 2^levels) go through the XYZZ bucket pass, which balances any bucket-size distribution.
 //
 // Host/device shared: tests/host builds this with g++ (carry flag emulated) and checks it against the oracle.
@@ -51,13 +54,7 @@ struct AffLevel {
   // level's output stores and (levels >= 1) its operand loads are whole contiguous runs (3 KB / 6 KB per warp and step)
   // instead of 32 streams 6 KB apart, which DRAM sees as random 32-byte accesses.
   uint32_t lane_step;
-  // level-0 operand scratch (SCR variants, else null): [T][2 * sizeof(Affine) / 16][nthreads] 16-byte chunks.  Pass 1
-  // gathers both operands of every output ONCE from the window tables (sign applied) and parks them here, thread-
-  // contiguous; pass 2 streams them back instead of gathering the same two random 96-byte points a second time.
-  uint4* opnd;
-  uint32_t U;  // outputs per inversion: a thread's T outputs are processed in sub-batches of U (0: one batch of T)
-  Fq* inv;            // [nthreads] chain inverses (split kernels: written by phase 1, read by phase 2)
-  uint32_t* cls_ctr;  // phase classes (null: off): per-SM arrival counters, a CTA's class = its arrival number on its SM mod 4
+  Fq* inv;  // [nthreads] chain inverses (split form: written by the phase-1 kernel, read by the phase-2 kernel)
 };
 
 struct AffMap {
@@ -190,61 +187,11 @@ B2M_HD AffKind aff_classify(const Affine<Fq>& P, const Affine<Fq>& Q, Fq* den) {
   return AFF_ADD;
 }
 
-// ---- operand scratch (SCR variants): element (k, t) is 2 * sizeof(Affine) / 16 chunks of 16 bytes, chunk-major so that a
-// warp's accesses to one chunk are 512 contiguous bytes --------------------------------------------------------------
-template <class Fq>
-B2M_HD void aff_opnd_store(uint4* opnd, size_t nth, uint32_t k, uint32_t t, const Affine<Fq>& P, const Affine<Fq>& Q) {
-  constexpr int CP = 2 * Fq::N / 4;  // 16-byte chunks per point
-  const uint32_t* p = reinterpret_cast<const uint32_t*>(&P);
-  const uint32_t* q = reinterpret_cast<const uint32_t*>(&Q);
-  uint4* dst = opnd + (size_t)k * (2 * CP) * nth + t;
-#pragma unroll
-  for (int c = 0; c < CP; c++) {
-    uint4 v;
-    v.x = p[4 * c]; v.y = p[4 * c + 1]; v.z = p[4 * c + 2]; v.w = p[4 * c + 3];
-    dst[(size_t)c * nth] = v;
-  }
-#pragma unroll
-  for (int c = 0; c < CP; c++) {
-    uint4 v;
-    v.x = q[4 * c]; v.y = q[4 * c + 1]; v.z = q[4 * c + 2]; v.w = q[4 * c + 3];
-    dst[(size_t)(CP + c) * nth] = v;
-  }
-}
-template <class Fq>
-B2M_HD void aff_opnd_load(const uint4* opnd, size_t nth, uint32_t k, uint32_t t, Affine<Fq>* P, Affine<Fq>* Q) {
-  constexpr int CP = 2 * Fq::N / 4;
-  uint32_t* p = reinterpret_cast<uint32_t*>(P);
-  uint32_t* q = reinterpret_cast<uint32_t*>(Q);
-  const uint4* src = opnd + (size_t)k * (2 * CP) * nth + t;
-#pragma unroll
-  for (int c = 0; c < CP; c++) {
-    const uint4 v = src[(size_t)c * nth];
-    p[4 * c] = v.x; p[4 * c + 1] = v.y; p[4 * c + 2] = v.z; p[4 * c + 3] = v.w;
-  }
-#pragma unroll
-  for (int c = 0; c < CP; c++) {
-    const uint4 v = src[(size_t)(CP + c) * nth];
-    q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
-  }
-}
-
-// ---- arithmetic: thread t adds the planned pairs of its T outputs, one shared inversion per sub-batch ----------------
-// PF = 1: load the next iteration's operands before the current iteration's multiplications in BOTH passes (costs ~50
-// registers, so fewer resident warps); PF = 2: in the denominator pass only (free: that pass is far below the register
-// high-water mark of the addition pass); PF = 0: loads are issued at use and latency is hidden by occupancy alone.
-// SCR (level 0): gather each operand once -- pass 1 loads the full points, parks them in A.opnd, pass 2 streams them.
-//
-// Sub-batches and phase classes.  Every thread does the same amount of work and every CTA of a wave starts at the same
-// time, so the warps that share an SM sub-partition march through the three phases in lock-step: all of them in the
-// memory-bound denominator pass (multiplier mostly idle), all of them in the ALU-only inversion (multiplier idle), all of
-// them in the multiplier-bound addition pass (3 of 4 waiting for the pipe) -- ncu showed the multiplier busy only ~60 %
-// of the time with every individual pipe far from saturated.  So a thread cuts its T outputs into sub-batches of A.U
-// outputs, each with its own prefix chain and inversion, and the FIRST sub-batch is shortened by the warp's phase class
-// (`cls` in 0..3, different for the CTAs that are co-resident on an SM): co-resident warps are then a quarter of a cycle
-// apart, and one warp's denominator pass / inversion runs under the other warps' multiplications.
-template <class Fq, int PF, bool SCR>
-B2M_HD void aff_level_thread(const AffLevel<Fq>& A, const Affine<Fq>* base, uint32_t t, uint32_t cls = 3) {
+// ---- arithmetic: thread t adds the planned pairs of its T outputs with one shared inversion -----------------------
+// PF: load the next iteration's operands before the current iteration's multiplications (costs ~50 registers, so fewer
+// resident warps); without it the loads are issued at use and latency is hidden by occupancy alone.
+template <class Fq, bool PF>
+B2M_HD void aff_level_thread(const AffLevel<Fq>& A, const Affine<Fq>* base, uint32_t t) {
   const uint32_t total = B2M_AFF_LDG32(A.off_out + A.B);
   const AffMap mp = aff_map(A, t, total);
   if (!mp.cnt) return;
@@ -252,186 +199,122 @@ B2M_HD void aff_level_thread(const AffLevel<Fq>& A, const Affine<Fq>* base, uint
   const size_t nth = A.nthreads;
   const uint4* meta = A.meta + t;
   Fq* pref = A.pref + t;
-  const uint32_t U = A.U ? A.U : A.T;
-  uint32_t first = (U * ((cls & 3u) + 1u)) / 4u;
-  if (first == 0) first = 1;
-  for (uint32_t kb = 0, ke = first < cnt ? first : cnt; kb < cnt; kb = ke, ke = (cnt - ke > U) ? ke + U : cnt) {
-    // ---- pass 1 over [kb, ke): denominators, running product ------------------------------------
-    Fq run = Fq::one();
-    if (SCR) {
-      uint4 m = meta[(size_t)kb * nth];
-      Affine<Fq> Pn, Qn;
-      if (PF) {
-        Pn = aff_ld(base, m.x);
-        Qn = aff_ld(base, m.y);
-      }
-      for (uint32_t k = kb; k < ke; k++) {
-        const uint4 mc = m;
-        Affine<Fq> P, Q;
-        if (PF) {
-          P = Pn;
-          Q = Qn;
-        } else {
-          P = aff_ld(base, mc.x);
-          Q = aff_ld(base, mc.y);
-        }
-        if (k + 1 < ke) {
-          m = meta[(size_t)(k + 1) * nth];
-          if (PF) {
-            Pn = aff_ld(base, m.x);
-            Qn = aff_ld(base, m.y);
-          }
-        }
-        P = aff_signed(P, mc.x);
-        Q = aff_signed(Q, mc.y);
-        aff_opnd_store(A.opnd, nth, k, t, P, Q);
-        Fq den = Fq::one();
-        if (mc.w) {
-          Fq d;
-          const AffKind kind = aff_classify(P, Q, &d);
-          if (kind == AFF_ADD || kind == AFF_DBL) den = d;
-        }
-        run = k > kb ? run * den : den;
-        B2M_AFF_ST(pref + (size_t)k * nth, run);
-      }
-    } else {
-      uint4 m = meta[(size_t)kb * nth];
-      uint4 m1 = ke - kb > 1 ? meta[(size_t)(kb + 1) * nth] : m;
-      Fq x1, x2;
-      if (PF) {
-        x1 = aff_ldx(base, m.x);
-        x2 = aff_ldx(base, m.y);
-      }
-      for (uint32_t k = kb; k < ke; k++) {
-        const uint4 mc = m;
-        Fq c1, c2;
-        if (PF) {
-          c1 = x1;
-          c2 = x2;
-        } else {
-          c1 = aff_ldx(base, mc.x);
-          c2 = aff_ldx(base, mc.y);
-        }
-        if (k + 1 < ke) {  // the plan runs two outputs ahead, (PF) the operands one
-          m = m1;
-          if (k + 2 < ke) m1 = meta[(size_t)(k + 2) * nth];
-          if (PF) {
-            x1 = aff_ldx(base, m.x);
-            x2 = aff_ldx(base, m.y);
-          }
-        }
-        Fq den = Fq::one();
-        if (mc.w) {
-          if (c1.is_zero() || c2.is_zero() || c1 == c2) {  // rare: infinity, doubling or cancellation
-            Fq d;
-            const AffKind kind = aff_classify(aff_signed(aff_ld(base, mc.x), mc.x), aff_signed(aff_ld(base, mc.y), mc.y), &d);
-            if (kind == AFF_ADD || kind == AFF_DBL) den = d;
-          } else {
-            den = c2 - c1;
-          }
-        }
-        run = k > kb ? run * den : den;
-        B2M_AFF_ST(pref + (size_t)k * nth, run);
-      }
+  // ---- pass 1: denominators, running product ----------------------------------------------------
+  Fq run = Fq::one();
+  {
+    uint4 m = meta[0];
+    uint4 m1 = cnt > 1 ? meta[nth] : m;
+    Fq x1, x2;
+    if (PF) {
+      x1 = aff_ldx(base, m.x);
+      x2 = aff_ldx(base, m.y);
     }
-    // ---- one inversion per sub-batch (the product of non-zero denominators is never zero) ---------
-    Fq inv = run.inverse_fast();
-    // ---- pass 2 over [kb, ke): walk back, peel one denominator at a time ---------------------------
-    {
-      constexpr bool PF2 = PF == 1 && !SCR;
-      uint4 m = meta[(size_t)(ke - 1) * nth];
-      uint4 m1 = ke - kb > 1 ? meta[(size_t)(ke - 2) * nth] : m;
-      Affine<Fq> Pn, Qn;
-      Fq pfn = run;  // product of the denominators before the output (read for k > kb only)
-      if (PF2) {
-        Pn = aff_ld(base, m.x);
-        Qn = aff_ld(base, m.y);
-        if (ke - kb > 1) pfn = B2M_AFF_LD(pref + (size_t)(ke - 2) * nth);
+    for (uint32_t k = 0; k < cnt; k++) {
+      const uint4 mc = m;
+      Fq c1, c2;
+      if (PF) {
+        c1 = x1;
+        c2 = x2;
+      } else {
+        c1 = aff_ldx(base, mc.x);
+        c2 = aff_ldx(base, mc.y);
       }
-      for (uint32_t k = ke; k-- > kb;) {
-        const uint4 mc = m;
-        Affine<Fq> P, Q;
-        Fq pf = run;
-        if (PF2) {
-          P = Pn;
-          Q = Qn;
-          pf = pfn;
+      if (k + 1 < cnt) {  // the plan runs two outputs ahead, (PF) the operands one
+        m = m1;
+        if (k + 2 < cnt) m1 = meta[(size_t)(k + 2) * nth];
+        if (PF) {
+          x1 = aff_ldx(base, m.x);
+          x2 = aff_ldx(base, m.y);
+        }
+      }
+      Fq den = Fq::one();
+      if (mc.w) {
+        if (c1.is_zero() || c2.is_zero() || c1 == c2) {  // rare: infinity, doubling or cancellation
+          Fq d;
+          const AffKind kind = aff_classify(aff_signed(aff_ld(base, mc.x), mc.x), aff_signed(aff_ld(base, mc.y), mc.y), &d);
+          if (kind == AFF_ADD || kind == AFF_DBL) den = d;
         } else {
-          if (SCR) {
-            aff_opnd_load(A.opnd, nth, k, t, &P, &Q);
+          den = c2 - c1;
+        }
+      }
+      run = k ? run * den : den;
+      B2M_AFF_ST(pref + (size_t)k * nth, run);
+    }
+  }
+  // ---- one inversion per thread (the product of non-zero denominators is never zero) ---------------------
+  Fq inv = run.inverse_fast();
+  // ---- pass 2: walk back, peel one denominator at a time ----------------------------------------------
+  {
+    uint4 m = meta[(size_t)(cnt - 1) * nth];
+    uint4 m1 = cnt > 1 ? meta[(size_t)(cnt - 2) * nth] : m;
+    Affine<Fq> Pn, Qn;
+    Fq pfn = run;  // product of the denominators before the output (read for k > 0 only)
+    if (PF) {
+      Pn = aff_ld(base, m.x);
+      Qn = aff_ld(base, m.y);
+      if (cnt > 1) pfn = B2M_AFF_LD(pref + (size_t)(cnt - 2) * nth);
+    }
+    for (uint32_t k = cnt; k-- > 0;) {
+      const uint4 mc = m;
+      Affine<Fq> P, Q;
+      Fq pf = run;
+      if (PF) {
+        P = Pn;
+        Q = Qn;
+        pf = pfn;
+      } else {
+        P = aff_ld(base, mc.x);
+        Q = aff_ld(base, mc.y);
+        if (k > 0) pf = B2M_AFF_LD(pref + (size_t)(k - 1) * nth);
+      }
+      P = aff_signed(P, mc.x);
+      Q = aff_signed(Q, mc.y);
+      if (k > 0) {
+        m = m1;
+        if (k > 1) m1 = meta[(size_t)(k - 2) * nth];
+        if (PF) {
+          Pn = aff_ld(base, m.x);
+          Qn = aff_ld(base, m.y);
+          if (k > 1) pfn = B2M_AFF_LD(pref + (size_t)(k - 2) * nth);
+        }
+      }
+      Affine<Fq> R = P;
+      if (mc.w) {
+        Fq den;
+        const AffKind kind = aff_classify(P, Q, &den);
+        if (kind == AFF_COPY_Q) {
+          R = Q;
+        } else if (kind == AFF_INF) {
+          R = Affine<Fq>::inf();
+        } else if (kind != AFF_COPY_P) {
+          Fq dinv = inv;
+          if (k > 0) dinv = inv * pf;
+          inv = inv * den;
+          Fq lam;
+          if (kind == AFF_ADD) {
+            lam = (Q.y - P.y) * dinv;
+            R.x = lam.sqr() - P.x - Q.x;
           } else {
-            P = aff_ld(base, mc.x);
-            Q = aff_ld(base, mc.y);
+            const Fq xx = P.x.sqr();
+            lam = (xx.dbl() + xx) * dinv;
+            R.x = lam.sqr() - P.x.dbl();
           }
-          if (k > kb) pf = B2M_AFF_LD(pref + (size_t)(k - 1) * nth);
+          R.y = lam * (P.x - R.x) - P.y;
         }
-        if (!SCR) {  // (the scratch holds the points with the sign applied)
-          P = aff_signed(P, mc.x);
-          Q = aff_signed(Q, mc.y);
-        }
-        if (k > kb) {
-          m = m1;
-          if (k > kb + 1) m1 = meta[(size_t)(k - 2) * nth];
-          if (PF2) {
-            Pn = aff_ld(base, m.x);
-            Qn = aff_ld(base, m.y);
-            if (k > kb + 1) pfn = B2M_AFF_LD(pref + (size_t)(k - 2) * nth);
-          }
-        }
-        Affine<Fq> R = P;
-        if (mc.w) {
-          Fq den;
-          const AffKind kind = aff_classify(P, Q, &den);
-          if (kind == AFF_COPY_Q) {
-            R = Q;
-          } else if (kind == AFF_INF) {
-            R = Affine<Fq>::inf();
-          } else if (kind != AFF_COPY_P) {
-            Fq dinv = inv;
-            if (k > kb) dinv = inv * pf;
-            inv = inv * den;
-            Fq lam;
-            if (kind == AFF_ADD) {
-              lam = (Q.y - P.y) * dinv;
-              R.x = lam.sqr() - P.x - Q.x;
-            } else {
-              const Fq xx = P.x.sqr();
-              lam = (xx.dbl() + xx) * dinv;
-              R.x = lam.sqr() - P.x.dbl();
-            }
-            R.y = lam * (P.x - R.x) - P.y;
-          }
-        }
-        const uint32_t o = mp.o0 + k * mp.step;
-        B2M_AFF_ST(&A.out[o].x, R.x);
-        B2M_AFF_ST(&A.out[o].y, R.y);
-        if (A.out_refs) {
-          uint2 r;
-          r.x = o;
-          r.y = mc.z;  // window 0: `out` is addressed directly
-          A.out_refs[o] = r;
-        }
+      }
+      const uint32_t o = mp.o0 + k * mp.step;
+      B2M_AFF_ST(&A.out[o].x, R.x);
+      B2M_AFF_ST(&A.out[o].y, R.y);
+      if (A.out_refs) {
+        uint2 r;
+        r.x = o;
+        r.y = mc.z;  // window 0: `out` is addressed directly
+        A.out_refs[o] = r;
       }
     }
   }
 }
 
-// ---- ILP variant (opt-in, B2M_MSM_AFFINE_CTAS / _UPPER = 6; not the default: unmeasured at the end of round 1) ------
-// The default thread function above runs ONE dependent multiplication chain in the denominator pass and a chain of
-// four in the addition pass, so a warp rarely has two multiplications in flight.  This variant
-// keeps TWO interleaved prefix chains (even and odd outputs) and handles two outputs per loop iteration, so every
-// multiplication has an independent twin -- the regime in which the XYZZ kernel reaches 90 % of the multiplier peak
-// with 8 warps per SM.  pref[k] holds the product of the denominators of outputs k, k - 2, k - 4, ... (own chain).
-template <class Fq>
-B2M_HD Fq aff_den_or_one(const Affine<Fq>* base, const uint4& m, const Fq& x1, const Fq& x2) {
-  if (!m.w) return Fq::one();
-  if (x1.is_zero() || x2.is_zero() || x1 == x2) {  // rare: infinity, doubling or cancellation
-    Fq den;
-    const AffKind kind = aff_classify(aff_signed(aff_ld(base, m.x), m.x), aff_signed(aff_ld(base, m.y), m.y), &den);
-    return (kind == AFF_ADD || kind == AFF_DBL) ? den : Fq::one();
-  }
-  return x2 - x1;
-}
 // one output given the inverse of its denominator; returns the denominator (one() if the output needs none)
 template <class Fq>
 B2M_HD Affine<Fq> aff_finish(const Affine<Fq>& P, const Affine<Fq>& Q, bool pair, const Fq& dinv, Fq* den_out) {
@@ -465,65 +348,6 @@ B2M_HD void aff_store_out(const AffLevel<Fq>& A, uint32_t o, const Affine<Fq>& R
     r.x = o;
     r.y = bucket;
     A.out_refs[o] = r;
-  }
-}
-
-template <class Fq>
-B2M_HD void aff_level_thread_ilp(const AffLevel<Fq>& A, const Affine<Fq>* base, uint32_t t) {
-  const uint32_t total = B2M_AFF_LDG32(A.off_out + A.B);
-  const AffMap mp = aff_map(A, t, total);
-  if (!mp.cnt) return;
-  const uint32_t cnt = mp.cnt;
-  const size_t nth = A.nthreads;
-  const uint4* meta = A.meta + t;
-  Fq* pref = A.pref + t;
-  // ---- pass 1: two prefix chains -------------------------------------------------------------------
-  Fq run0 = Fq::one(), run1 = Fq::one();  // chains of the even / odd outputs
-  for (uint32_t k = 0; k < cnt; k += 2) {
-    const bool two = k + 1 < cnt;
-    const uint4 m0 = meta[(size_t)k * nth];
-    const uint4 m1 = two ? meta[(size_t)(k + 1) * nth] : m0;
-    const Fq a1 = aff_ldx(base, m0.x), a2 = aff_ldx(base, m0.y);
-    const Fq b1 = aff_ldx(base, m1.x), b2 = aff_ldx(base, m1.y);
-    const Fq d0 = aff_den_or_one(base, m0, a1, a2);
-    const Fq d1 = two ? aff_den_or_one(base, m1, b1, b2) : Fq::one();
-    run0 = run0 * d0;
-    run1 = run1 * d1;
-    B2M_AFF_ST(pref + (size_t)k * nth, run0);
-    if (two) B2M_AFF_ST(pref + (size_t)(k + 1) * nth, run1);
-  }
-  // ---- one inversion for both chains -------------------------------------------------------------------
-  const Fq inv_all = (run0 * run1).inverse_fast();
-  Fq inv0 = inv_all * run1, inv1 = inv_all * run0;
-  // ---- pass 2: walk back two outputs (one of each chain) at a time ------------------------------------------
-  uint32_t k = cnt;
-  if (cnt & 1u) {  // the top output has no twin: it is the last one of the even chain
-    k--;
-    const uint4 m = meta[(size_t)k * nth];
-    const Affine<Fq> P = aff_signed(aff_ld(base, m.x), m.x), Q = aff_signed(aff_ld(base, m.y), m.y);
-    Fq dinv = inv0;
-    if (k >= 2) dinv = inv0 * B2M_AFF_LD(pref + (size_t)(k - 2) * nth);
-    Fq den;
-    const Affine<Fq> R = aff_finish(P, Q, m.w != 0, dinv, &den);
-    inv0 = inv0 * den;
-    aff_store_out(A, mp.o0 + k * mp.step, R, m.z);
-  }
-  while (k >= 2) {
-    k -= 2;  // outputs k + 1 (odd chain) and k (even chain)
-    const uint4 m1 = meta[(size_t)(k + 1) * nth];
-    const uint4 m0 = meta[(size_t)k * nth];
-    const Affine<Fq> P1 = aff_signed(aff_ld(base, m1.x), m1.x), Q1 = aff_signed(aff_ld(base, m1.y), m1.y);
-    const Affine<Fq> P0 = aff_signed(aff_ld(base, m0.x), m0.x), Q0 = aff_signed(aff_ld(base, m0.y), m0.y);
-    Fq dinv1 = inv1, dinv0 = inv0;
-    if (k + 1 >= 2) dinv1 = inv1 * B2M_AFF_LD(pref + (size_t)(k - 1) * nth);
-    if (k >= 2) dinv0 = inv0 * B2M_AFF_LD(pref + (size_t)(k - 2) * nth);
-    Fq den1, den0;
-    const Affine<Fq> R1 = aff_finish(P1, Q1, m1.w != 0, dinv1, &den1);
-    const Affine<Fq> R0 = aff_finish(P0, Q0, m0.w != 0, dinv0, &den0);
-    inv1 = inv1 * den1;
-    inv0 = inv0 * den0;
-    aff_store_out(A, mp.o0 + (k + 1) * mp.step, R1, m1.z);
-    aff_store_out(A, mp.o0 + k * mp.step, R0, m0.z);
   }
 }
 

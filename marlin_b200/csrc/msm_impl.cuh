@@ -198,22 +198,10 @@ __global__ void __launch_bounds__(256) msm_affine_plan_kernel(const AffLevel<Fq>
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < A.nthreads) aff_plan_thread<Fq, L0>(A, t);
 }
-template <class Fq, int MINB, int PF, bool SCR>
+template <class Fq, int MINB, bool PF>
 __global__ void __launch_bounds__(128, MINB) msm_affine_level_kernel(const AffLevel<Fq> A, const Affine<Fq>* __restrict__ base) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  // phase class = arrival number of this CTA on its SM (mod 4): the CTAs resident together on an SM always differ
-  __shared__ uint32_t s_cls;
-  if (threadIdx.x == 0) {
-    uint32_t c = 3u;
-    if (A.cls_ctr) {
-      uint32_t smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      c = atomicAdd(A.cls_ctr + (smid & 1023u), 1u) & 3u;
-    }
-    s_cls = c;
-  }
-  __syncthreads();
-  if (t < A.nthreads) aff_level_thread<Fq, PF, SCR>(A, base, t, s_cls);
+  if (t < A.nthreads) aff_level_thread<Fq, PF>(A, base, t);
 }
 
 // software-pipelined variant (msm_affine.cuh aff_level_thread_sp): variants 8 (3 CTAs/SM), 9 (2), 10 (4)
@@ -221,13 +209,6 @@ template <class Fq, int MINB, int PHASE, bool PIPE = true>
 __global__ void __launch_bounds__(128, MINB) msm_affine_level_sp_kernel(const AffLevel<Fq> A, const Affine<Fq>* __restrict__ base) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < A.nthreads) aff_level_thread_sp<Fq, PHASE, PIPE>(A, base, t);
-}
-
-// opt-in two-chain variant (msm_affine.cuh aff_level_thread_ilp): B2M_MSM_AFFINE_CTAS / B2M_MSM_AFFINE_CTAS_UPPER = 6
-template <class Fq>
-__global__ void __launch_bounds__(128, 2) msm_affine_level_ilp_kernel(const AffLevel<Fq> A, const Affine<Fq>* __restrict__ base) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < A.nthreads) aff_level_thread_ilp<Fq>(A, base, t);
 }
 
 // Partials are ordered by bucket (they follow the sorted references).  The first partial of each bucket
@@ -495,13 +476,7 @@ Msm<Fr, Fq>::Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, const Affine<
   if (const char* e = getenv("B2M_MSM_AFFINE_CTAS_UPPER")) affine_ctas_upper = atoi(e);
   if (const char* e = getenv("B2M_MSM_AFFINE_MIN_REFS")) affine_min_refs = (size_t)atoll(e);
   if (const char* e = getenv("B2M_MSM_AFFINE_MAP")) affine_map = atoi(e);
-  if (const char* e = getenv("B2M_MSM_AFFINE_SCR")) affine_scr = atoi(e);
-  if (const char* e = getenv("B2M_MSM_AFFINE_U")) affine_U = atoi(e);
-  if (const char* e = getenv("B2M_MSM_AFFINE_CLASSES")) affine_classes = atoi(e);
-  if (affine_U < 0) affine_U = 0;
-  cls_ctr = DBuf<uint32_t>(cx, 1024);  // per-SM arrival counters of the level kernels (never reset: only the low bits matter)
-  cls_ctr.zero();
-  cx.sync();
+
   if (affine_levels < 0) affine_levels = 0;
   if (affine_levels > MSM_MAX_AFFINE_LEVELS) affine_levels = MSM_MAX_AFFINE_LEVELS;
   if (affine_T < 1) affine_T = 1;
@@ -612,7 +587,7 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
     DBuf<Affine<Fq>> lvl_pts[2];
     DBuf<uint32_t> lvl_off[2], lvl_cnt;
     DBuf<uint2> lvl_refs;
-    DBuf<uint4> lvl_meta, lvl_opnd;
+    DBuf<uint4> lvl_meta;
     DBuf<Fq> lvl_pref, lvl_inv;
     if (LV > 0) {
       lvl_pts[0] = DBuf<Affine<Fq>>(cx, bound[1]);
@@ -623,7 +598,6 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       lvl_meta = DBuf<uint4>(cx, slots_l0);
       lvl_pref = DBuf<Fq>(cx, slots_l0);
       lvl_inv = DBuf<Fq>(cx, slots_l0 / affine_T + 1);
-      if (affine_scr) lvl_opnd = DBuf<uint4>(cx, slots_l0 * (2 * sizeof(Affine<Fq>) / 16));
     }
     buckets.zero();  // empty buckets are never written: all-zero XYZZ is the point at infinity
     cudaEvent_t ev_ready, ev_sorted[MSM_MAX_BATCH], ev_acc[MSM_MAX_BATCH];
@@ -679,46 +653,35 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
           exclusive_scan_u32(cx, lvl_cnt.p, off_out, (size_t)B + 1);
           const uint32_t lane_step = affine_map ? 32u : 1u;
           const uint32_t nthreads = (uint32_t)(lane_step * ((bound[l + 1] + (size_t)lane_step * affine_T - 1) / ((size_t)lane_step * affine_T)));
-          const bool scr = l == 0 && affine_scr;
           AffLevel<Fq> A{tables.p, stride, sorted[s].p, l > 0 ? lvl_pts[(l - 1) & 1].p : nullptr, off_in, off_out, B, lvl_pts[l & 1].p,
-                         l == LV - 1 ? lvl_refs.p : nullptr, lvl_pref.p, lvl_meta.p, (uint32_t)affine_T, nthreads, lane_step,
-                         scr ? lvl_opnd.p : nullptr, (uint32_t)affine_U, lvl_inv.p, affine_classes ? cls_ctr.p : nullptr};
+                         l == LV - 1 ? lvl_refs.p : nullptr, lvl_pref.p, lvl_meta.p, (uint32_t)affine_T, nthreads, lane_step, lvl_inv.p};
           if (l == 0)
             msm_affine_plan_kernel<Fq, true><<<div_up(nthreads, 256), 256, 0, cx.stream>>>(A);
           else
             msm_affine_plan_kernel<Fq, false><<<div_up(nthreads, 256), 256, 0, cx.stream>>>(A);
           const Affine<Fq>* base = l == 0 ? tables.p : lvl_pts[(l - 1) & 1].p;
           const unsigned grid = div_up(nthreads, 128);
-          // kernel variant: 4 (default) / 5 = plain loads, compiled for that many resident CTAs per SM; 3 = operands
-          // prefetched in both passes (3 CTAs/SM); 7 = prefetched in the denominator pass only; 6 = two chains (ILP)
+          // Kernel variant (B2M_MSM_AFFINE_CTAS / _UPPER; every variant gives the same bytes, profiles/r02_level_kernel_notes.md):
+          //   4 (default), 5: fused kernel, loads at use, compiled for that many resident CTAs per SM; 3: operands prefetched (3 CTAs/SM)
+          //   8, 9: fused, branch-free and software-pipelined addition pass (3 / 2 CTAs/SM)
+          //   11-13: split -- denominator pass + inversion at 5 CTAs/SM, then the addition pass pipelined at 3 / 2 CTAs/SM or plain at 4
           const int variant = l == 0 ? affine_ctas : affine_ctas_upper;
           static const char* const lvl_names[MSM_MAX_AFFINE_LEVELS] = {"msm_aff_level0", "msm_aff_level1", "msm_aff_level2", "msm_aff_level3",
                                                                        "msm_aff_level4", "msm_aff_level5"};
           const size_t spk = cx.span_begin(lvl_names[l], (double)n);
-          if (scr) {
-            if (variant == 7) msm_affine_level_kernel<Fq, 4, 2, true><<<grid, 128, 0, cx.stream>>>(A, base);
-            else msm_affine_level_kernel<Fq, 4, 0, true><<<grid, 128, 0, cx.stream>>>(A, base);
-          } else {
-            switch (variant) {
-              case 6: msm_affine_level_ilp_kernel<Fq><<<grid, 128, 0, cx.stream>>>(A, base); break;
-              case 8: msm_affine_level_sp_kernel<Fq, 3, 0><<<grid, 128, 0, cx.stream>>>(A, base); break;
-              case 9: msm_affine_level_sp_kernel<Fq, 2, 0><<<grid, 128, 0, cx.stream>>>(A, base); break;
-              // split form: denominator pass + inversion at high occupancy, then the addition pass on its own
-              case 11: case 12: case 13: case 14: case 15: case 16: {
-                if (variant <= 13) msm_affine_level_sp_kernel<Fq, 5, 1><<<grid, 128, 0, cx.stream>>>(A, base);
-                else msm_affine_level_sp_kernel<Fq, 6, 1><<<grid, 128, 0, cx.stream>>>(A, base);
-                const int v2 = (variant - 11) % 3;
-                if (v2 == 0) msm_affine_level_sp_kernel<Fq, 3, 2><<<grid, 128, 0, cx.stream>>>(A, base);
-                else if (v2 == 1) msm_affine_level_sp_kernel<Fq, 2, 2><<<grid, 128, 0, cx.stream>>>(A, base);
-                else msm_affine_level_sp_kernel<Fq, 4, 2, false><<<grid, 128, 0, cx.stream>>>(A, base);
-                cx.launches++;
-                break;
-              }
-              case 3: msm_affine_level_kernel<Fq, 3, 1, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
-              case 5: msm_affine_level_kernel<Fq, 5, 0, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
-              case 7: msm_affine_level_kernel<Fq, 4, 2, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
-              default: msm_affine_level_kernel<Fq, 4, 0, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
-            }
+          switch (variant) {
+            case 3: msm_affine_level_kernel<Fq, 3, true><<<grid, 128, 0, cx.stream>>>(A, base); break;
+            case 5: msm_affine_level_kernel<Fq, 5, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
+            case 8: msm_affine_level_sp_kernel<Fq, 3, 0><<<grid, 128, 0, cx.stream>>>(A, base); break;
+            case 9: msm_affine_level_sp_kernel<Fq, 2, 0><<<grid, 128, 0, cx.stream>>>(A, base); break;
+            case 11: case 12: case 13:
+              msm_affine_level_sp_kernel<Fq, 5, 1><<<grid, 128, 0, cx.stream>>>(A, base);
+              if (variant == 11) msm_affine_level_sp_kernel<Fq, 3, 2><<<grid, 128, 0, cx.stream>>>(A, base);
+              else if (variant == 12) msm_affine_level_sp_kernel<Fq, 2, 2><<<grid, 128, 0, cx.stream>>>(A, base);
+              else msm_affine_level_sp_kernel<Fq, 4, 2, false><<<grid, 128, 0, cx.stream>>>(A, base);
+              cx.launches++;
+              break;
+            default: msm_affine_level_kernel<Fq, 4, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
           }
           cx.span_end(spk);
           B2M_CHECK_LAUNCH();

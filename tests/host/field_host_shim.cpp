@@ -57,7 +57,7 @@ extern "C" void curve_op(int curve, int which, const uint32_t* pts, const uint8_
 // references, then every bucket's remaining points are summed with XYZZ additions (what the XYZZ pass does).
 template <class Fq>
 static void run_levels(const uint32_t* tables, const uint32_t* refs, const uint32_t* off0, uint32_t B, int levels, uint32_t T, uint32_t* out_buckets,
-                       int variant, int interleaved, int scr, uint32_t U) {
+                       int variant, int interleaved) {
   const Affine<Fq>* tab = reinterpret_cast<const Affine<Fq>*>(tables);
   const uint2* sorted = reinterpret_cast<const uint2*>(refs);
   std::vector<uint32_t> off_in(off0, off0 + B + 1), off_out(B + 1);
@@ -71,28 +71,22 @@ static void run_levels(const uint32_t* tables, const uint32_t* refs, const uint3
     const uint32_t nthreads = lane_step * ((total + lane_step * T - 1) / (lane_step * T));
     out.assign(total, Affine<Fq>::inf());
     out_refs.assign(total, uint2{0, 0});
-    std::vector<Fq> pref((size_t)T * (nthreads ? nthreads : 1));
+    std::vector<Fq> pref((size_t)T * (nthreads ? nthreads : 1)), invs(nthreads ? nthreads : 1);
     std::vector<uint4> meta((size_t)T * (nthreads ? nthreads : 1));
-    std::vector<Fq> invs(nthreads ? nthreads : 1);
-    const bool use_scr = scr && l == 0;
-    std::vector<uint4> opnd(use_scr ? (size_t)T * (nthreads ? nthreads : 1) * (2 * sizeof(Affine<Fq>) / 16) : 1);
     AffLevel<Fq> A{tab, 0, sorted, in.data(), off_in.data(), off_out.data(), B, out.data(), l == levels - 1 ? out_refs.data() : nullptr,
-                   pref.data(), meta.data(), T, nthreads, lane_step, use_scr ? opnd.data() : nullptr, U, invs.data(), nullptr};
+                   pref.data(), meta.data(), T, nthreads, lane_step, invs.data()};
     for (uint32_t t = 0; t < nthreads; t++) {
       if (l == 0) aff_plan_thread<Fq, true>(A, t); else aff_plan_thread<Fq, false>(A, t);
     }
     for (uint32_t t = 0; t < nthreads; t++) {
       const Affine<Fq>* base = l == 0 ? tab : in.data();
-      const uint32_t cls = U ? (t / 3u) & 3u : 3u;  // phase class (any value must give the same sums)
-      if (use_scr) {
-        if (T & 1) aff_level_thread<Fq, 2, true>(A, base, t, cls); else aff_level_thread<Fq, 0, true>(A, base, t, cls);
-      } else if (variant == 1) aff_level_thread_ilp<Fq>(A, base, t);
-      else if (variant == 3) aff_level_thread_sp<Fq, 0>(A, base, t);
+      // variant 0: fused kernel's thread function (odd T: with operand prefetch); 3: software-pipelined; 4 / 5: its split
+      // (two-kernel) form with the pipelined / plain addition pass
+      if (variant == 3) aff_level_thread_sp<Fq, 0>(A, base, t);
       else if (variant == 4) { aff_level_thread_sp<Fq, 1>(A, base, t); aff_level_thread_sp<Fq, 2>(A, base, t); }
       else if (variant == 5) { aff_level_thread_sp<Fq, 1>(A, base, t); aff_level_thread_sp<Fq, 2, false>(A, base, t); }
-      else if (variant == 2) aff_level_thread<Fq, 2, false>(A, base, t, cls);
-      else if (T & 1) aff_level_thread<Fq, 1, false>(A, base, t, cls);
-      else aff_level_thread<Fq, 0, false>(A, base, t, cls);
+      else if (T & 1) aff_level_thread<Fq, true>(A, base, t);
+      else aff_level_thread<Fq, false>(A, base, t);
     }
     in.swap(out);
     off_in = off_out;
@@ -108,7 +102,7 @@ static void run_levels(const uint32_t* tables, const uint32_t* refs, const uint3
   for (uint32_t b = 0; b < B; b++) ob[b] = acc[b].to_affine();
 }
 extern "C" void affine_levels_host(int curve, const uint32_t* tables, const uint32_t* refs, const uint32_t* off0, uint32_t B, int levels, uint32_t T,
-                                   uint32_t* out_buckets, int variant, int interleaved, int scr, uint32_t U) {
-  if (curve == 0) run_levels<FqBls>(tables, refs, off0, B, levels, T, out_buckets, variant, interleaved, scr, U);
-  else run_levels<FqBn>(tables, refs, off0, B, levels, T, out_buckets, variant, interleaved, scr, U);
+                                   uint32_t* out_buckets, int variant, int interleaved) {
+  if (curve == 0) run_levels<FqBls>(tables, refs, off0, B, levels, T, out_buckets, variant, interleaved);
+  else run_levels<FqBn>(tables, refs, off0, B, levels, T, out_buckets, variant, interleaved);
 }

@@ -145,28 +145,20 @@ def test_batched_affine_levels(hostlib, ci, curve):
             want.append(acc)
         refs_a = np.array(refs if refs else [0, 0], dtype=np.uint32)
         off_a = np.array(off, dtype=np.uint32)
-        # variant 0: default thread function (odd T: with operand prefetch), 1: the two-chain ILP one, 2: prefetch in the
-        # denominator pass only; mapping 0 = blocked, 1 = warp-interleaved; scr = level 0 parks its operands in the scratch
-        cases = [(0, 1, 0, 0, 0), (1, 1, 0, 0, 0), (1, 4, 0, 0, 0), (2, 3, 0, 0, 0), (3, 8, 0, 0, 0), (7, 5, 0, 0, 0), (3, 64, 0, 0, 0),
-                 (1, 1, 1, 0, 0), (2, 3, 1, 0, 0), (3, 8, 1, 0, 0), (4, 5, 1, 0, 0), (3, 64, 1, 0, 0),
-                 (1, 1, 0, 1, 0), (1, 4, 0, 1, 0), (2, 3, 0, 1, 0), (3, 2, 0, 1, 0), (4, 1, 2, 1, 0), (3, 8, 2, 1, 0), (7, 5, 0, 1, 0),
-                 (2, 3, 1, 1, 0), (3, 2, 1, 1, 0), (4, 5, 1, 1, 0), (3, 64, 1, 1, 0),
-                 (1, 1, 0, 1, 1), (2, 2, 0, 1, 1), (3, 3, 0, 1, 1), (3, 4, 2, 0, 1), (4, 1, 1, 1, 1), (3, 8, 0, 0, 1)]
-        cases = [c + (0,) for c in cases]
-        # variant 3: the software-pipelined thread function
-        cases += [(1, 1, 5, 1, 0, 0), (2, 3, 5, 1, 0, 0), (3, 8, 5, 0, 0, 0), (3, 64, 5, 1, 0, 0),  # 5: split, plain addition pass
-                  (1, 1, 4, 1, 0, 0), (2, 3, 4, 1, 0, 0), (3, 8, 4, 0, 0, 0), (3, 64, 4, 1, 0, 0),  # 4: its split (two-kernel) form
-                  (1, 1, 3, 1, 0, 0), (1, 2, 3, 1, 0, 0), (2, 3, 3, 1, 0, 0), (3, 8, 3, 1, 0, 0), (4, 5, 3, 0, 0, 0), (7, 4, 3, 1, 0, 0), (3, 64, 3, 1, 0, 0)]
-        # sub-batches of U outputs per inversion with per-thread phase classes (first sub-batch shortened)
-        cases += [(3, 8, 0, 1, 0, 4), (3, 8, 0, 1, 1, 3), (2, 7, 2, 1, 0, 2), (3, 64, 0, 1, 0, 32), (3, 64, 0, 1, 1, 16), (4, 5, 0, 0, 0, 1),
-                  (3, 9, 1, 1, 0, 4), (2, 6, 0, 0, 1, 8)]
-        for levels, T, variant, interleaved, scr, U in cases:
+        # (levels, T, variant, mapping): variant 0 = the fused kernel's thread function (odd T: with operand prefetch), 3 = the
+        # software-pipelined one, 4 / 5 = its split (two-kernel) form with the pipelined / plain addition pass; mapping 0 =
+        # blocked, 1 = warp-interleaved
+        cases = [(0, 1, 0, 0), (1, 1, 0, 0), (1, 4, 0, 0), (2, 3, 0, 0), (3, 8, 0, 0), (7, 5, 0, 0), (3, 64, 0, 0),
+                 (1, 1, 0, 1), (1, 4, 0, 1), (2, 3, 0, 1), (3, 2, 0, 1), (4, 1, 0, 1), (3, 8, 0, 1), (7, 5, 0, 1), (3, 64, 0, 1),
+                 (1, 1, 3, 1), (1, 2, 3, 1), (2, 3, 3, 1), (3, 8, 3, 1), (4, 5, 3, 0), (7, 4, 3, 1), (3, 64, 3, 1),
+                 (1, 1, 4, 1), (2, 3, 4, 1), (3, 8, 4, 0), (3, 64, 4, 1), (1, 1, 5, 1), (2, 3, 5, 1), (3, 8, 5, 0), (3, 64, 5, 1)]
+        for levels, T, variant, interleaved in cases:
             out = np.zeros(B * 2 * n32, dtype=np.uint32)
             hostlib.affine_levels_host(ci, tab_l.ctypes.data_as(ctypes.c_void_p), refs_a.ctypes.data_as(ctypes.c_void_p),
                                        off_a.ctypes.data_as(ctypes.c_void_p), B, levels, T, out.ctypes.data_as(ctypes.c_void_p), variant,
-                                       interleaved, scr, U)
+                                       interleaved)
             for b in range(B):
                 x = sum(int(out[b * 2 * n32 + i]) << (32 * i) for i in range(n32))
                 y = sum(int(out[b * 2 * n32 + n32 + i]) << (32 * i) for i in range(n32))
                 got = None if x == 0 and y == 0 else (fq.from_mont(x), fq.from_mont(y))
-                assert got == want[b], (trial, levels, T, variant, interleaved, scr, U, b)
+                assert got == want[b], (trial, levels, T, variant, interleaved, b)

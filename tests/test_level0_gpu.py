@@ -189,15 +189,12 @@ def test_msm_skewed_scalars(b2m_ctx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("levels,T,variant,upper,mapping,scr,sub", [(a, b, c, d, e, f, 0) for a, b, c, d, e, f in [
-    (1, 1, 4, 4, 1, 0), (2, 3, 4, 4, 1, 0), (3, 64, 4, 4, 1, 0), (4, 5, 3, 3, 1, 0), (6, 2, 5, 5, 1, 0),  # every kernel variant, default mapping
-    (3, 4, 6, 6, 1, 0), (2, 7, 6, 4, 1, 0), (3, 64, 4, 6, 1, 0), (3, 5, 7, 7, 1, 0),                      # two-chain (ILP), pass-1 prefetch
-    (3, 64, 4, 4, 1, 1), (2, 3, 7, 4, 1, 1), (4, 1, 4, 6, 1, 1),                                           # level 0 through the operand scratch
-    (3, 64, 4, 4, 0, 0), (2, 5, 6, 6, 0, 0), (3, 3, 3, 7, 0, 1)]] + [                                      # blocked mapping
-    (3, 64, 8, 8, 1, 0, 0), (2, 3, 9, 9, 1, 0, 0), (4, 1, 9, 8, 0, 0, 0), (1, 7, 8, 8, 1, 0, 0),  # software-pipelined kernels
-    (3, 64, 11, 13, 1, 0, 0), (2, 3, 12, 14, 1, 0, 0), (4, 1, 15, 16, 0, 0, 0), (3, 5, 13, 11, 1, 0, 0), (1, 64, 16, 16, 1, 0, 0),  # split: two kernels per level
-    (3, 64, 4, 4, 1, 0, 32), (3, 64, 4, 4, 1, 1, 16), (2, 8, 7, 3, 1, 0, 3), (4, 128, 4, 4, 1, 0, 48), (3, 5, 4, 4, 0, 0, 2)])  # sub-batches + phase classes
-def test_msm_affine_levels_forced(b2m_ctx, monkeypatch, levels, T, variant, upper, mapping, scr, sub):
+@pytest.mark.parametrize("levels,T,variant,upper,mapping", [
+    (1, 1, 4, 4, 1), (2, 3, 4, 4, 1), (3, 64, 4, 4, 1), (4, 5, 3, 3, 1), (6, 2, 5, 5, 1),   # fused kernel variants, default (interleaved) mapping
+    (3, 64, 8, 8, 1), (2, 3, 9, 9, 1), (4, 1, 9, 8, 0), (1, 7, 8, 8, 1),                    # software-pipelined kernels
+    (3, 64, 11, 13, 1), (2, 3, 12, 11, 1), (4, 1, 13, 12, 0), (3, 5, 13, 11, 1), (1, 64, 12, 12, 1),  # split: two kernels per level
+    (3, 64, 4, 4, 0), (2, 5, 3, 5, 0)])                                                     # blocked mapping
+def test_msm_affine_levels_forced(b2m_ctx, monkeypatch, levels, T, variant, upper, mapping):
     """The batched-affine levels (csrc/msm_affine.cuh) are skipped for small MSMs; force them on (any size, odd
     batch lengths, every kernel variant) over the inputs that hit their special cases: colliding bases (P + P,
     P - P inside a bucket, at level 0 and above), zero / equal / tiny scalars, buckets of every parity."""
@@ -206,9 +203,6 @@ def test_msm_affine_levels_forced(b2m_ctx, monkeypatch, levels, T, variant, uppe
     monkeypatch.setenv("B2M_MSM_AFFINE_CTAS", str(variant))
     monkeypatch.setenv("B2M_MSM_AFFINE_CTAS_UPPER", str(upper))
     monkeypatch.setenv("B2M_MSM_AFFINE_MAP", str(mapping))
-    monkeypatch.setenv("B2M_MSM_AFFINE_SCR", str(scr))
-    monkeypatch.setenv("B2M_MSM_AFFINE_U", str(sub))
-    monkeypatch.setenv("B2M_MSM_AFFINE_CLASSES", "1" if sub else "0")
     monkeypatch.setenv("B2M_MSM_AFFINE_MIN_REFS", "0")
     curve = BLS12_381
     r = curve.fr.p
