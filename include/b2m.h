@@ -46,10 +46,13 @@ enum { B2M_CURVE_BLS12_381 = 0, B2M_CURVE_BN254 = 1 };
 enum { B2M_PC_MARLIN_KZG10 = 0, B2M_PC_SONIC_KZG10 = 1 };
 /* stream ciphers behind `RngCore`: rand 0.8 StdRng (= ChaCha12, `ark_std::test_rng`) and
  * rand_chacha::ChaChaRng (= ChaCha20). */
-enum { B2M_RNG_CHACHA12 = 12, B2M_RNG_CHACHA20 = 20, B2M_RNG_CHACHA8 = 8 };
+enum { B2M_RNG_CHACHA12 = 12, B2M_RNG_CHACHA20 = 20, B2M_RNG_CHACHA8 = 8,
+       /* any other `RngCore`: the library pulls every random u64 through a host callback (b2m_rng::next_u64) */
+       B2M_RNG_CALLBACK = 1 };
 
 typedef struct b2m_ctx b2m_ctx;
 typedef struct b2m_srs b2m_srs;
+typedef struct b2m_ck b2m_ck;
 typedef struct b2m_index b2m_index;
 
 const char* b2m_last_error(void);
@@ -113,13 +116,21 @@ int b2m_srs_msm(b2m_srs* srs, size_t base_off, const uint64_t* scalars, size_t n
 int b2m_g1_powers(b2m_ctx* ctx, int curve, const uint64_t* g_xy, const uint64_t* beta, size_t n,
                   uint64_t* out_powers_xy);
 
-/* The caller's `zk_rng: &mut R` (reference src/lib.rs:154).  A ChaCha block RNG is described by
- * its key and word position so the mask polynomial (3|H| draws, src/ahp/prover.rs:371) can
- * be sampled on the device bit-exactly; word_pos is updated to the position after the call. */
+/* The caller's `zk_rng: &mut R` / `rng: Option<&mut dyn RngCore>` (reference src/lib.rs:154,125).  Two forms:
+ *  - kind = B2M_RNG_CHACHA8/12/20, the fast path for the generators the reference's tests and benches use
+ *    (`ark_std::test_rng()` = ChaCha12, `rand_chacha::ChaChaRng` = ChaCha20): the stream is described by its key and
+ *    word position, so the mask polynomial (3|H| draws, src/ahp/prover.rs:371) is sampled on the device bit-exactly;
+ *    word_pos is updated to the position after the call.
+ *  - kind = B2M_RNG_CALLBACK, any other generator: every `next_u64()` the reference would issue is pulled, in the
+ *    reference's order, through `next_u64(state)` on the calling thread (a Rust shim passes a trampoline over
+ *    `&mut dyn RngCore`); the mask polynomial is then drawn on the host and uploaded once.  key / word_pos are unused.
+ * Draw order and counts are those of ark-ff 0.3 `F::rand` (4 u64 limbs per attempt, low limb first, rejection sampling). */
 typedef struct {
-  int kind;          /* B2M_RNG_CHACHA* */
+  int kind;          /* B2M_RNG_CHACHA* or B2M_RNG_CALLBACK */
   uint8_t key[32];
   uint64_t word_pos; /* number of 32-bit words already consumed from the stream */
+  uint64_t (*next_u64)(void* state); /* B2M_RNG_CALLBACK only */
+  void* state;
 } b2m_rng;
 
 /* ---- Level 1: polynomial-commitment ABI --------------------------------------------------------- */
@@ -151,6 +162,48 @@ int b2m_pc_open(b2m_srs* srs, int pc_variant, size_t n_polys, const uint64_t* co
                 const uint64_t* shifted_rands, size_t rand_stride, int64_t max_degree_bound,
                 const uint64_t* point, const uint64_t* opening_challenge, uint64_t* out_w_xy,
                 int* out_has_random_v, uint64_t* out_random_v);
+
+/* Replaces `PC::trim(pp, supported_degree, supported_hiding_bound, enforced_degree_bounds)` (reference src/lib.rs:112-121)
+ * for PC = MarlinKZG10 / SonicKZG10 [U ark-poly-commit 0.3 marlin_pc/mod.rs, sonic_pc/mod.rs trim].  The device-resident
+ * SRS already holds every power, so trimming selects and validates: supported_degree <= max_degree, the hiding bound needs
+ * powers 0..=supported_hiding_bound+1 of gamma*G (SonicKZG10 additionally max_degree - bound + 0..=hiding_bound+1 per enforced
+ * bound), every enforced bound <= supported_degree.  The committer key borrows the SRS (destroy the key first).
+ * Errors: B2M_ERR_DEGREE_TOO_LARGE (TrimmingDegreeTooLarge / bound above the supported degree), B2M_ERR_INVALID_ARG. */
+int b2m_trim(b2m_srs* srs, int pc_variant, size_t supported_degree, size_t supported_hiding_bound,
+             const uint64_t* enforced_degree_bounds, size_t n_bounds, b2m_ck** out);
+void b2m_ck_destroy(b2m_ck* ck);
+size_t b2m_ck_supported_degree(const b2m_ck* ck);
+/* `vk.degree_bounds_and_shift_powers` of MarlinKZG10's verifier key: shift power for an enforced bound =
+ * powers_of_g[max_degree - bound] (affine x||y Montgomery).  B2M_ERR_INVALID_ARG if the bound is not enforced. */
+int b2m_ck_shift_power(const b2m_ck* ck, uint64_t bound, uint64_t* out_xy);
+/* `PC::commit(ck, ..)` with the committer key's checks [U ark-poly-commit check_degrees_and_bounds]: a polynomial longer than
+ * supported_degree + 1 coefficients, a degree bound that is not one of the enforced bounds (or below the polynomial's degree)
+ * or a hiding bound above the supported one fail with B2M_ERR_DEGREE_TOO_LARGE / B2M_ERR_INVALID_ARG.  Otherwise identical
+ * to b2m_pc_commit. */
+int b2m_ck_commit(b2m_ck* ck, size_t n_polys, const uint64_t* const* coeffs, const size_t* n_coeffs,
+                  const int64_t* degree_bounds, const int64_t* hiding_bounds, b2m_rng* rng, uint64_t* out_comm_xy,
+                  uint64_t* out_shifted_xy, uint64_t* out_rand, uint64_t* out_shifted_rand, size_t rand_stride);
+
+/* Replaces `PC::open_combinations(ck, lc_s, polynomials, commitments, query_set, opening_challenge, rands, rng)`
+ * (reference src/lib.rs:292-302) [U ark-poly-commit 0.3 marlin_pc / sonic_pc open_combinations_individual_opening_challenges].
+ *   polynomials / rands       : as for b2m_pc_commit / b2m_pc_open (hiding[i] != 0 iff polynomial i was committed hiding).
+ *   linear combinations       : LC l has the terms [lc_term_off[l], lc_term_off[l+1]); term t is lc_coeff[t] (Montgomery Fr)
+ *                               times polynomial lc_poly[t], or the constant `LCTerm::One` when lc_poly[t] < 0 (which only
+ *                               shifts the evaluation and is skipped, as upstream does).  The caller passes the LCs in the
+ *                               order of their labels (upstream sorts them, reference src/ahp/mod.rs:219).  An LC may carry a
+ *                               degree bound only if it is a single polynomial with coefficient one
+ *                               (else B2M_ERR_INVALID_ARG: EquationHasDegreeBounds).
+ *   query set                 : pairs (query_lc[q], query_point[q]); points[] are the distinct evaluation points in the order
+ *                               of their point labels (upstream iterates a BTreeMap keyed by the label: "beta" < "gamma").
+ *   opening challenge         : xi; challenge k is xi^k, restarting at k = 0 for every point.
+ * Output: one `kzg10::Proof {w, random_v}` per point -- `BatchLCProof.proof` (its `evals` field is None upstream). */
+int b2m_ck_open_combinations(b2m_ck* ck, size_t n_polys, const uint64_t* const* coeffs, const size_t* n_coeffs,
+                             const int64_t* degree_bounds, const int* hiding, const uint64_t* rands,
+                             const uint64_t* shifted_rands, size_t rand_stride, size_t n_lcs, const size_t* lc_term_off,
+                             const int64_t* lc_poly, const uint64_t* lc_coeff, size_t n_queries, const size_t* query_lc,
+                             const size_t* query_point, size_t n_points, const uint64_t* points,
+                             const uint64_t* opening_challenge, uint64_t* out_w_xy, int* out_has_random_v,
+                             uint64_t* out_random_v);
 
 /* ---- Level 2: prover ABI ---------------------------------------------------------------- */
 

@@ -28,8 +28,13 @@ class Matrix(ctypes.Structure):
     _fields_ = [("row_ptr", ctypes.c_void_p), ("col", ctypes.c_void_p), ("coeff", ctypes.c_void_p)]
 
 
+NEXT_U64 = ctypes.CFUNCTYPE(ctypes.c_uint64, ctypes.c_void_p)
+RNG_CALLBACK = 1
+
+
 class Rng(ctypes.Structure):
-    _fields_ = [("kind", ctypes.c_int), ("key", ctypes.c_uint8 * 32), ("word_pos", ctypes.c_uint64)]
+    _fields_ = [("kind", ctypes.c_int), ("key", ctypes.c_uint8 * 32), ("word_pos", ctypes.c_uint64), ("next_u64", NEXT_U64),
+                ("state", ctypes.c_void_p)]
 
 
 _lib = None
@@ -70,6 +75,14 @@ def lib():
         L.b2m_g1_powers.argtypes = [vp, ci, vp, vp, sz, vp]
         L.b2m_pc_commit.argtypes = [vp, ci, sz, vp, vp, vp, vp, P(Rng), vp, vp, vp, vp, sz]
         L.b2m_pc_open.argtypes = [vp, ci, sz, vp, vp, vp, vp, vp, sz, ctypes.c_int64, vp, vp, vp, P(ci), vp]
+        L.b2m_trim.argtypes = [vp, ci, sz, sz, vp, sz, P(vp)]
+        L.b2m_ck_destroy.argtypes = [vp]
+        L.b2m_ck_destroy.restype = None
+        L.b2m_ck_supported_degree.argtypes = [vp]
+        L.b2m_ck_supported_degree.restype = sz
+        L.b2m_ck_shift_power.argtypes = [vp, u64, vp]
+        L.b2m_ck_commit.argtypes = [vp, sz, vp, vp, vp, vp, P(Rng), vp, vp, vp, vp, sz]
+        L.b2m_ck_open_combinations.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, sz, sz, vp, vp, vp, sz, vp, vp, sz, vp, vp, vp, vp, vp]
         if hasattr(L, "b2m_index_create"):
             L.b2m_index_create.argtypes = [vp, ci, sz, sz, sz, P(Matrix), P(Matrix), P(Matrix), P(vp)]
             L.b2m_index_destroy.argtypes = [vp]

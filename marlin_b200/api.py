@@ -68,6 +68,43 @@ class ZkRng:
         return int(self.c.word_pos)
 
 
+class CallbackRng:
+    """Any other `RngCore` behind the C ABI (B2M_RNG_CALLBACK): `next_u64` is a Python callable returning the generator's next
+    64-bit output; the library pulls every random value the reference would draw through it, in the reference's order."""
+
+    def __init__(self, next_u64):
+        self._fn = next_u64
+        self._cb = _lib.NEXT_U64(lambda _state: int(self._fn()) & 0xFFFFFFFFFFFFFFFF)  # kept alive with the object
+        self.c = _lib.Rng()
+        self.c.kind = _lib.RNG_CALLBACK
+        self.c.next_u64 = self._cb
+        self.c.state = None
+
+    @property
+    def word_pos(self):
+        return None
+
+
+class CommitterKey:
+    """`PC::CommitterKey` after `PC::trim` (b2m_ck): a validated view of the device-resident SRS."""
+
+    def __init__(self, srs, handle, pc, supported_degree, hiding_bound, degree_bounds):
+        self.srs, self.handle, self.pc = srs, handle, pc
+        self.supported_degree, self.hiding_bound, self.degree_bounds = supported_degree, hiding_bound, sorted(set(degree_bounds))
+
+    def shift_power(self, bound):
+        """MarlinKZG10 verifier key entry for an enforced bound: powers_of_g[max_degree - bound] (affine limbs)."""
+        lq = _lib.LIMBS[self.srs.curve_id][1]
+        out = np.zeros(2 * lq, dtype=np.uint64)
+        _lib.check(_lib.lib().b2m_ck_shift_power(self.handle, bound, _lib.ptr(out)))
+        return out
+
+    def close(self):
+        if self.handle:
+            _lib.lib().b2m_ck_destroy(self.handle)
+            self.handle = None
+
+
 class UniversalSRS:
     """`PC::UniversalParams`, device resident (b2m_srs): G1 powers + the gamma powers the PC needs."""
 
@@ -169,6 +206,53 @@ class Marlin:
                                     _lib.ptr(gi), len(gi), window_bits, ctypes.byref(h)))
         return UniversalSRS(self.ctx, self.curve_id, h, len(powers_limbs) - 1, powers_limbs, gamma_limbs, [int(i) for i in gi])
 
+    # -- PC::trim (Level 1) ---------------------------------------------------------------------------------
+    def trim(self, srs, supported_degree, supported_hiding_bound, enforced_degree_bounds=()):
+        """`PC::trim(pp, supported_degree, supported_hiding_bound, enforced_degree_bounds)` [reference src/lib.rs:112-121]
+        -> CommitterKey (the verifier key's G1 part is read with CommitterKey.shift_power)."""
+        L = _lib.lib()
+        h = ctypes.c_void_p()
+        b = np.asarray(sorted(enforced_degree_bounds), dtype=np.uint64)
+        _lib.check(L.b2m_trim(srs.handle, self.pc, supported_degree, supported_hiding_bound, _lib.ptr(b) if len(b) else None, len(b),
+                              ctypes.byref(h)))
+        return CommitterKey(srs, h, self.pc, supported_degree, supported_hiding_bound, [int(x) for x in b])
+
+    def open_combinations(self, ck, polys, rands, shifted_rands, lcs, query_set, points, challenge_limbs):
+        """`PC::open_combinations` [reference src/lib.rs:292-302].  polys: (coeff limbs, degree_bound, hiding_bound) as for
+        `commit`; rands / shifted_rands as returned by `commit`; lcs: list of term lists [(coeff Montgomery limbs (4,), poly index
+        or None for the constant term)], in label order; query_set: [(lc index, point index)]; points: (n_points, 4) Montgomery
+        limbs in point-label order.  Returns [(w affine limbs, random_v limbs or None)] per point."""
+        L = _lib.lib()
+        n = len(polys)
+        lq = _lib.LIMBS[self.curve_id][1]
+        arrs = [np.ascontiguousarray(p[0], dtype=np.uint64) for p in polys]
+        ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        lens = (ctypes.c_size_t * n)(*[len(a) for a in arrs])
+        db = (ctypes.c_int64 * n)(*[-1 if p[1] is None else p[1] for p in polys])
+        hid = (ctypes.c_int * n)(*[0 if p[2] is None else 1 for p in polys])
+        rands = np.ascontiguousarray(rands, dtype=np.uint64)
+        shifted_rands = np.ascontiguousarray(shifted_rands, dtype=np.uint64)
+        offs, lp, lcf = [0], [], []
+        for terms in lcs:
+            for coeff, idx in terms:
+                lp.append(-1 if idx is None else idx)
+                lcf.append(np.asarray(coeff, dtype=np.uint64).reshape(4))
+            offs.append(len(lp))
+        offs_a = (ctypes.c_size_t * len(offs))(*offs)
+        lp_a = (ctypes.c_int64 * len(lp))(*lp)
+        lcf_a = np.ascontiguousarray(np.stack(lcf), dtype=np.uint64)
+        ql = (ctypes.c_size_t * len(query_set))(*[q[0] for q in query_set])
+        qp = (ctypes.c_size_t * len(query_set))(*[q[1] for q in query_set])
+        pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 4)
+        npts = len(pts)
+        w = np.zeros((npts, 2 * lq), dtype=np.uint64)
+        has = (ctypes.c_int * npts)()
+        rv = np.zeros((npts, 4), dtype=np.uint64)
+        _lib.check(L.b2m_ck_open_combinations(ck.handle, n, ptrs, lens, db, hid, _lib.ptr(rands), _lib.ptr(shifted_rands), rands.shape[1],
+                                              len(lcs), offs_a, lp_a, _lib.ptr(lcf_a), len(query_set), ql, qp, npts, _lib.ptr(pts),
+                                              _lib.ptr(np.ascontiguousarray(challenge_limbs, dtype=np.uint64)), _lib.ptr(w), has, _lib.ptr(rv)))
+        return [(w[i], rv[i] if has[i] else None) for i in range(npts)]
+
     # -- PC::commit (Level 1) ------------------------------------------------------------------------------
     def commit(self, srs, polys, zk_rng=None):
         """`PC::commit(ck, polynomials, rng)` [reference src/lib.rs:125,172,193,213].  polys: list of
@@ -187,8 +271,11 @@ class Marlin:
         rand = np.zeros((n, 4, 4), dtype=np.uint64)
         srand = np.zeros((n, 4, 4), dtype=np.uint64)
         rp = ctypes.byref(zk_rng.c) if zk_rng is not None else None
-        _lib.check(L.b2m_pc_commit(srs.handle, self.pc, n, ptrs, lens, db, hb, rp, _lib.ptr(comm), _lib.ptr(shifted), _lib.ptr(rand),
-                                   _lib.ptr(srand), 4))
+        if isinstance(srs, CommitterKey):  # `PC::commit(ck, ..)` with the committer key's degree / bound checks
+            _lib.check(L.b2m_ck_commit(srs.handle, n, ptrs, lens, db, hb, rp, _lib.ptr(comm), _lib.ptr(shifted), _lib.ptr(rand), _lib.ptr(srand), 4))
+        else:
+            _lib.check(L.b2m_pc_commit(srs.handle, self.pc, n, ptrs, lens, db, hb, rp, _lib.ptr(comm), _lib.ptr(shifted), _lib.ptr(rand),
+                                       _lib.ptr(srand), 4))
         return comm, shifted, rand, srand
 
     def open(self, srs, polys, rands, shifted_rands, point_limbs, challenge_limbs, max_degree_bound=None):

@@ -3,6 +3,7 @@
 #include "capi_types.cuh"
 #include "prover.cuh"
 #include "comm.cuh"
+#include <algorithm>
 
 namespace b2m {
 thread_local std::string g_last_error;
@@ -24,10 +25,11 @@ int b2m_ctx_create(int device, b2m_ctx** out) {
 
 void b2m_ctx_destroy(b2m_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->cx.device);
-  cudaStreamSynchronize(ctx->cx.stream);
-  if (ctx->cx.comm) NcclApi::get().CommDestroy(static_cast<ncclComm_t>(ctx->cx.comm));
-  delete ctx;
+  if (ctx->children > 0) {  // SRSs still borrow this context: freed with the last of them
+    ctx->dead = true;
+    return;
+  }
+  b2m_release_ctx(ctx);
 }
 
 unsigned long long b2m_ctx_launches(const b2m_ctx* ctx) { return ctx ? ctx->cx.launches : 0; }
@@ -92,14 +94,17 @@ int b2m_srs_create(b2m_ctx* ctx, int curve, const uint64_t* powers_of_g, size_t 
     B2M_REQUIRE(curve == B2M_CURVE_BLS12_381 || curve == B2M_CURVE_BN254, B2M_ERR_INVALID_ARG, "unknown curve id");
     ctx->cx.use();
     *out = new b2m_srs(ctx, curve, powers_of_g, n_g, powers_of_gamma_g, gamma_indices, n_gamma, window_bits);
+    ctx->children++;
   });
 }
 
 void b2m_srs_destroy(b2m_srs* srs) {
   if (!srs) return;
-  srs->ctx->cx.use();
-  cudaStreamSynchronize(srs->ctx->cx.stream);
-  delete srs;
+  if (srs->children > 0) {  // indexes / committer keys still borrow this SRS: freed with the last of them
+    srs->dead = true;
+    return;
+  }
+  b2m_release_srs(srs);
 }
 
 size_t b2m_srs_size(const b2m_srs* srs) { return srs ? srs->n_g : 0; }
@@ -114,6 +119,22 @@ int b2m_srs_msm(b2m_srs* srs, size_t base_off, const uint64_t* scalars, size_t n
     else srs->bn->run_host(base_off, scalars, n, out_xy, out_is_inf);
   });
 }
+
+}  // extern "C"
+void b2m_release_ctx(b2m_ctx* ctx) {
+  cudaSetDevice(ctx->cx.device);
+  cudaStreamSynchronize(ctx->cx.stream);
+  if (ctx->cx.comm) NcclApi::get().CommDestroy(static_cast<ncclComm_t>(ctx->cx.comm));
+  delete ctx;
+}
+void b2m_release_srs(b2m_srs* srs) {
+  b2m_ctx* ctx = srs->ctx;
+  ctx->cx.use();
+  cudaStreamSynchronize(ctx->cx.stream);
+  delete srs;
+  if (--ctx->children == 0 && ctx->dead) b2m_release_ctx(ctx);
+}
+extern "C" {
 
 int b2m_msm_g1(b2m_ctx* ctx, int curve, const uint64_t* bases_xy, const uint64_t* scalars, size_t n, uint64_t* out_xy,
                int* out_is_inf) {
@@ -148,7 +169,8 @@ int b2m_pc_commit(b2m_srs* srs, int pc_variant, size_t n_polys, const uint64_t* 
     B2M_REQUIRE(pc_variant == B2M_PC_MARLIN_KZG10 || pc_variant == B2M_PC_SONIC_KZG10, B2M_ERR_INVALID_ARG, "unknown PC variant");
     B2M_REQUIRE(pc_variant != B2M_PC_MARLIN_KZG10 || (out_shifted_xy && out_shifted_rand), B2M_ERR_INVALID_ARG,
                 "MarlinKZG10 needs the shifted output buffers");
-    B2M_REQUIRE(rng == nullptr || rng->kind == B2M_RNG_CHACHA8 || rng->kind == B2M_RNG_CHACHA12 || rng->kind == B2M_RNG_CHACHA20,
+    B2M_REQUIRE(rng == nullptr || rng->kind == B2M_RNG_CHACHA8 || rng->kind == B2M_RNG_CHACHA12 || rng->kind == B2M_RNG_CHACHA20 ||
+                    (rng->kind == B2M_RNG_CALLBACK && rng->next_u64 != nullptr),
                 B2M_ERR_MISSING_RNG, "unsupported rng kind");
     srs->ctx->cx.use();
     if (srs->curve == B2M_CURVE_BLS12_381)
@@ -179,6 +201,104 @@ int b2m_pc_open(b2m_srs* srs, int pc_variant, size_t n_polys, const uint64_t* co
   });
 }
 
+int b2m_trim(b2m_srs* srs, int pc_variant, size_t supported_degree, size_t supported_hiding_bound, const uint64_t* enforced_degree_bounds,
+             size_t n_bounds, b2m_ck** out) {
+  return guard([&] {
+    B2M_REQUIRE(srs && out && (enforced_degree_bounds || n_bounds == 0), B2M_ERR_INVALID_ARG, "null argument");
+    B2M_REQUIRE(pc_variant == B2M_PC_MARLIN_KZG10 || pc_variant == B2M_PC_SONIC_KZG10, B2M_ERR_INVALID_ARG, "unknown PC variant");
+    const size_t D = srs->n_g - 1;
+    B2M_REQUIRE(supported_degree >= 1 && supported_degree <= D, B2M_ERR_DEGREE_TOO_LARGE, "supported degree %zu out of range (max degree %zu)",
+                supported_degree, D);  // TrimmingDegreeTooLarge / DegreeIsZero
+    std::unique_ptr<b2m_ck> ck(new b2m_ck{srs, pc_variant, supported_degree, supported_hiding_bound, {}});
+    for (size_t k = 0; k < n_bounds; k++) {
+      B2M_REQUIRE(enforced_degree_bounds[k] <= supported_degree, B2M_ERR_DEGREE_TOO_LARGE, "enforced degree bound %llu exceeds the supported degree %zu",
+                  (unsigned long long)enforced_degree_bounds[k], supported_degree);
+      ck->bounds.push_back(enforced_degree_bounds[k]);
+    }
+    std::sort(ck->bounds.begin(), ck->bounds.end());
+    ck->bounds.erase(std::unique(ck->bounds.begin(), ck->bounds.end()), ck->bounds.end());
+    // the hiding powers this key will be asked for must be resident (throws B2M_ERR_INVALID_ARG naming the missing power)
+    for (size_t i = 0; i <= supported_hiding_bound + 1; i++) srs->gamma_slot(i);
+    if (pc_variant == B2M_PC_SONIC_KZG10)
+      for (uint64_t b : ck->bounds)
+        for (size_t i = 0; i <= supported_hiding_bound + 1; i++) srs->gamma_slot(D - b + i);
+    *out = ck.release();
+    srs->children++;
+  });
+}
+
+void b2m_ck_destroy(b2m_ck* ck) {
+  if (!ck) return;
+  b2m_srs* srs = ck->srs;
+  delete ck;
+  if (--srs->children == 0 && srs->dead) b2m_release_srs(srs);
+}
+
+size_t b2m_ck_supported_degree(const b2m_ck* ck) { return ck ? ck->supported_degree : 0; }
+
+int b2m_ck_shift_power(const b2m_ck* ck, uint64_t bound, uint64_t* out_xy) {
+  return guard([&] {
+    B2M_REQUIRE(ck && out_xy, B2M_ERR_INVALID_ARG, "null argument");
+    B2M_REQUIRE(ck->enforced(bound), B2M_ERR_INVALID_ARG, "degree bound %llu is not enforced by this committer key", (unsigned long long)bound);
+    b2m_srs* srs = ck->srs;
+    srs->ctx->cx.use();
+    const size_t slot = srs->n_g - 1 - bound;
+    if (srs->curve == B2M_CURVE_BLS12_381) srs->bls->read_power(slot, out_xy);
+    else srs->bn->read_power(slot, out_xy);
+  });
+}
+
+static void ck_check_polys(const b2m_ck* ck, size_t n_polys, const size_t* n_coeffs, const int64_t* degree_bounds, const int64_t* hiding_bounds) {
+  for (size_t i = 0; i < n_polys; i++) {
+    B2M_REQUIRE(n_coeffs[i] <= ck->supported_degree + 1, B2M_ERR_DEGREE_TOO_LARGE, "polynomial %zu has degree %zu, the committer key supports %zu", i,
+                n_coeffs[i] ? n_coeffs[i] - 1 : 0, ck->supported_degree);  // TooManyCoefficients
+    if (degree_bounds[i] >= 0)
+      B2M_REQUIRE(ck->enforced((uint64_t)degree_bounds[i]), B2M_ERR_INVALID_ARG, "polynomial %zu: degree bound %lld is not enforced by this committer key", i,
+                  (long long)degree_bounds[i]);  // UnsupportedDegreeBound
+    if (hiding_bounds && hiding_bounds[i] >= 0)
+      B2M_REQUIRE((size_t)hiding_bounds[i] <= ck->hiding_bound, B2M_ERR_INVALID_ARG, "polynomial %zu: hiding bound %lld above the supported %zu", i,
+                  (long long)hiding_bounds[i], ck->hiding_bound);  // HidingBoundToolarge
+  }
+}
+
+int b2m_ck_commit(b2m_ck* ck, size_t n_polys, const uint64_t* const* coeffs, const size_t* n_coeffs, const int64_t* degree_bounds,
+                  const int64_t* hiding_bounds, b2m_rng* rng, uint64_t* out_comm_xy, uint64_t* out_shifted_xy, uint64_t* out_rand,
+                  uint64_t* out_shifted_rand, size_t rand_stride) {
+  int rc = guard([&] {
+    B2M_REQUIRE(ck && n_coeffs && degree_bounds && hiding_bounds, B2M_ERR_INVALID_ARG, "null argument");
+    ck_check_polys(ck, n_polys, n_coeffs, degree_bounds, hiding_bounds);
+  });
+  if (rc != B2M_OK) return rc;
+  return b2m_pc_commit(ck->srs, ck->pc, n_polys, coeffs, n_coeffs, degree_bounds, hiding_bounds, rng, out_comm_xy, out_shifted_xy, out_rand,
+                       out_shifted_rand, rand_stride);
+}
+
+int b2m_ck_open_combinations(b2m_ck* ck, size_t n_polys, const uint64_t* const* coeffs, const size_t* n_coeffs, const int64_t* degree_bounds,
+                             const int* hiding, const uint64_t* rands, const uint64_t* shifted_rands, size_t rand_stride, size_t n_lcs,
+                             const size_t* lc_term_off, const int64_t* lc_poly, const uint64_t* lc_coeff, size_t n_queries, const size_t* query_lc,
+                             const size_t* query_point, size_t n_points, const uint64_t* points, const uint64_t* opening_challenge,
+                             uint64_t* out_w_xy, int* out_has_random_v, uint64_t* out_random_v) {
+  return guard([&] {
+    B2M_REQUIRE(ck && coeffs && n_coeffs && degree_bounds && hiding && rands && lc_term_off && lc_poly && lc_coeff && query_lc && query_point &&
+                    points && opening_challenge && out_w_xy && out_has_random_v && out_random_v,
+                B2M_ERR_INVALID_ARG, "null argument");
+    B2M_REQUIRE(n_polys >= 1 && n_lcs >= 1 && n_points >= 1 && n_queries >= 1, B2M_ERR_INVALID_ARG, "empty opening");
+    B2M_REQUIRE(ck->pc != B2M_PC_MARLIN_KZG10 || shifted_rands, B2M_ERR_INVALID_ARG, "MarlinKZG10 needs the shifted randomness");
+    ck_check_polys(ck, n_polys, n_coeffs, degree_bounds, nullptr);
+    for (size_t q = 0; q < n_queries; q++) B2M_REQUIRE(query_point[q] < n_points, B2M_ERR_INVALID_ARG, "query %zu names point %zu of %zu", q, query_point[q], n_points);
+    b2m_srs* srs = ck->srs;
+    srs->ctx->cx.use();
+    if (srs->curve == B2M_CURVE_BLS12_381)
+      pc_open_combinations_bls(srs, ck->pc, ck->max_bound(), n_polys, coeffs, n_coeffs, degree_bounds, hiding, rands, shifted_rands, rand_stride, n_lcs,
+                               lc_term_off, lc_poly, lc_coeff, n_queries, query_lc, query_point, n_points, points, opening_challenge, out_w_xy,
+                               out_has_random_v, out_random_v);
+    else
+      pc_open_combinations_bn(srs, ck->pc, ck->max_bound(), n_polys, coeffs, n_coeffs, degree_bounds, hiding, rands, shifted_rands, rand_stride, n_lcs,
+                              lc_term_off, lc_poly, lc_coeff, n_queries, query_lc, query_point, n_points, points, opening_challenge, out_w_xy,
+                              out_has_random_v, out_random_v);
+  });
+}
+
 // ---- Level 2 ----------------------------------------------------------------------------------
 struct b2m_index {
   b2m_srs* srs;
@@ -198,14 +318,17 @@ int b2m_index_create(b2m_srs* srs, int pc_variant, size_t num_constraints, size_
     else
       idx->impl.reset(make_index_bn(srs, pc_variant, num_constraints, num_variables, num_instance_variables, a, b, c));
     *out = idx.release();
+    srs->children++;
   });
 }
 
 void b2m_index_destroy(b2m_index* idx) {
   if (!idx) return;
-  idx->srs->ctx->cx.use();
-  cudaStreamSynchronize(idx->srs->ctx->cx.stream);
+  b2m_srs* srs = idx->srs;
+  srs->ctx->cx.use();
+  cudaStreamSynchronize(srs->ctx->cx.stream);
   delete idx;
+  if (--srs->children == 0 && srs->dead) b2m_release_srs(srs);
 }
 
 int b2m_index_vk_bytes(const b2m_index* idx, uint8_t* out, size_t cap, size_t* len) {

@@ -25,8 +25,12 @@ int guard(F&& f) {
 }
 }  // namespace b2m
 
+// Lifetimes: an index / committer key borrows its SRS, an SRS borrows its context.  Destroying a parent while children are
+// alive only marks it; the storage goes when the last child is destroyed, so no destroy order is a use-after-free.
 struct b2m_ctx {
   b2m::Ctx cx;
+  int children = 0;
+  bool dead = false;
   std::unique_ptr<b2m::Ntt<b2m::FrBls>> ntt_bls_;
   std::unique_ptr<b2m::Ntt<b2m::FrBn>> ntt_bn_;
   explicit b2m_ctx(int device) : cx(device) {}
@@ -42,6 +46,8 @@ struct b2m_ctx {
 
 struct b2m_srs {
   b2m_ctx* ctx;
+  int children = 0;
+  bool dead = false;
   int curve;
   size_t n_g, n_gamma;
   std::unique_ptr<b2m::Msm<b2m::FrBls, b2m::FqBls>> bls;
@@ -76,3 +82,20 @@ struct b2m_srs {
   size_t affine_min_refs() const { return bls ? bls->affine_min_refs : bn->affine_min_refs; }
 };
 
+
+// `PC::CommitterKey` after `PC::trim`: a validated view of the device-resident SRS
+struct b2m_ck {
+  b2m_srs* srs;
+  int pc;
+  size_t supported_degree, hiding_bound;
+  std::vector<uint64_t> bounds;  // enforced degree bounds, sorted
+  int64_t max_bound() const { return bounds.empty() ? -1 : (int64_t)bounds.back(); }
+  bool enforced(uint64_t b) const {
+    for (uint64_t x : bounds)
+      if (x == b) return true;
+    return false;
+  }
+};
+
+void b2m_release_ctx(b2m_ctx* ctx);
+void b2m_release_srs(b2m_srs* srs);

@@ -123,6 +123,22 @@ struct ChaChaHost {
   }
 };
 
+// The caller's rng behind the C ABI (include/b2m.h b2m_rng): a ChaCha stream position (device-samplable) or a host
+// callback standing for any `RngCore`.  `Rng` below is any type with next_u64().
+template <class RngDesc>
+struct ZkSource {
+  RngDesc* desc;
+  ChaChaHost cc;
+  bool callback;
+  explicit ZkSource(RngDesc* d) : desc(d), callback(d != nullptr && d->kind == 1 /* B2M_RNG_CALLBACK */) {
+    if (d && !callback) cc = ChaChaHost(d->key, d->kind, d->word_pos);
+  }
+  uint64_t next_u64() { return callback ? desc->next_u64(desc->state) : cc.next_u64(); }
+  void commit_position() {  // report the stream position back to the caller (ChaCha form)
+    if (desc && !callback) desc->word_pos = cc.word_pos;
+  }
+};
+
 // `F::rand(rng)` of ark-ff 0.3: rejection sampling on limbs; accepted limbs are the Montgomery form.
 template <class F, class Rng>
 F field_rand(Rng& rng) {

@@ -18,4 +18,13 @@ void pc_open_bn(b2m_srs* srs, int pc, size_t n_polys, const uint64_t* const* coe
   pc_open_impl<FrBn, FqBn>(srs, srs->ctx->ntt_bn(), *srs->bn, pc, n_polys, coeffs, n_coeffs, degree_bounds, rands, shifted_rands, rand_stride,
                            max_degree_bound, point, opening_challenge, out_w_xy, out_has_random_v, out_random_v);
 }
+void pc_open_combinations_bn(b2m_srs* srs, int pc, int64_t max_degree_bound, size_t n_polys, const uint64_t* const* coeffs, const size_t* n_coeffs,
+                              const int64_t* degree_bounds, const int* hiding, const uint64_t* rands, const uint64_t* shifted_rands, size_t rand_stride,
+                              size_t n_lcs, const size_t* lc_term_off, const int64_t* lc_poly, const uint64_t* lc_coeff, size_t n_queries,
+                              const size_t* query_lc, const size_t* query_point, size_t n_points, const uint64_t* points,
+                              const uint64_t* opening_challenge, uint64_t* out_w_xy, int* out_has_random_v, uint64_t* out_random_v) {
+  pc_open_combinations_impl<FrBn, FqBn>(srs, *srs->bn, pc, max_degree_bound, n_polys, coeffs, n_coeffs, degree_bounds, hiding, rands, shifted_rands,
+                                        rand_stride, n_lcs, lc_term_off, lc_poly, lc_coeff, n_queries, query_lc, query_point, n_points, points,
+                                        opening_challenge, out_w_xy, out_has_random_v, out_random_v);
+}
 }  // namespace b2m

@@ -81,6 +81,8 @@ struct Msm {
   void run_batch(const MsmJob<Fr, Fq>* jobs, int nj);
   // Level-0 ABI bodies (include/b2m.h): host scalars in, host affine point out.
   void run_host(size_t base_off, const uint64_t* scalars, size_t n, uint64_t* out_xy, int* out_is_inf);
+  // powers_of_g[i] (affine Montgomery limbs) back to the host: window-0 table entry, from the GPU that holds it
+  void read_power(size_t i, uint64_t* out_xy);
   static void g1_powers_host(Ctx& cx, const uint64_t* g_xy, const uint64_t* beta, size_t n, uint64_t* out);
 };
 

@@ -25,7 +25,7 @@ __device__ __forceinline__ Affine<Fq> ld_affine(const Affine<Fq>* p) {
 template <class Fq> __device__ __noinline__ void g1_add(XYZZ<Fq>& a, const XYZZ<Fq>& b) { a.add(b); }
 template <class Fq> __device__ __noinline__ void g1_add_mixed(XYZZ<Fq>& a, const Affine<Fq>& b) { a.add_mixed(b); }
 template <class Fq> __device__ __noinline__ void g1_dbl(XYZZ<Fq>& a) { a = a.dbl(); }
-template <class Fq> __device__ __noinline__ Fq fq_inverse(const Fq& a) { return a.inverse(); }
+template <class Fq> __device__ __noinline__ Fq fq_inverse(const Fq& a) { return a.inverse_fast(); }  // binary Euclid: ~1/5 of the Fermat ladder's latency
 template <class Fq> __device__ __noinline__ Affine<Fq> g1_to_affine(const XYZZ<Fq>& p) {
   if (p.is_inf()) return Affine<Fq>::inf();
   Fq izzz = fq_inverse(p.ZZZ);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128, MINB) msm_affine_level_sp_kernel(const Af
 // Partials are ordered by bucket (they follow the sorted references).  The first partial of each bucket
 // sums the ones that follow it and stores the bucket; a bucket cut into many partials (skewed scalar
 // distributions, e.g. a polynomial whose coefficients are nearly all equal) is queued for
-// msm_stitch_long_kernel, which reduces it with a whole block.
+// msm_stitch_runs_kernel, which reduces it with a whole warp.
 struct MsmLongRun {
   uint32_t first, last, bucket;  // partial slots [first, last]
 };
@@ -225,7 +225,7 @@ msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nthr
   // One thread per accumulate-thread u.  A run of partials starts either in u's tail slot (a bucket that
   // begins inside u's range and continues into u + 1) or in u's head slot when the bucket begins exactly at
   // u's first reference; u can hold only one of the two.  The common run is the pair (tail of u, head of
-  // u + 1): every lane does exactly one addition.  Longer runs go to msm_stitch_long_kernel.
+  // u + 1): every lane does exactly one addition.  Longer runs go to msm_stitch_runs_kernel.
   size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (u >= nthreads) return;
   uint32_t first = 2u * (uint32_t)u + 1u;
@@ -253,52 +253,38 @@ msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nthr
   g1_add(acc, ld_words(part_pt + last));
   st_words(buckets + b, acc);
 }
-// Runs longer than a pair (heavy buckets: e.g. the top window's digits of scalars < r only reach the low
-// 2^15 buckets).  One thread per queued run folds it serially -- all lanes busy, a handful of additions
-// each; runs of more than MSM_GIANT_SLOTS slots are re-queued for the block-per-run kernel.
-constexpr uint32_t MSM_GIANT_SLOTS = 256;
+// Runs longer than a pair (heavy buckets: with a short top window -- e.g. 3 bits at c = 18, which is what an 8-GPU
+// shard of a 2^20 key picks -- ALL references of that window land in a handful of buckets, each cut into hundreds of
+// partials).  One WARP per queued run: the lanes stride over the run's slots, then a 5-step tree through shared
+// memory.  (Round 1 folded runs of up to 256 slots serially in one thread: 256 dependent XYZZ additions, ~2 ms of
+// latency per MSM, the reason `msm_stitch` grew from 1.3 ms to 8-13 ms per proof on 4 and 8 GPUs.)
 template <class Fq>
 __global__ void __launch_bounds__(128)
-msm_stitch_long_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, const MsmLongRun* long_runs, const uint32_t* n_long,
-                       uint32_t long_cap, XYZZ<Fq>* buckets, MsmLongRun* giant_runs, uint32_t* n_giant) {
+msm_stitch_runs_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, const MsmLongRun* long_runs, const uint32_t* n_long,
+                       uint32_t long_cap, XYZZ<Fq>* buckets) {
+  __shared__ uint4 sm_raw[128 * sizeof(XYZZ<Fq>) / 16];
+  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(sm_raw) + (threadIdx.x & ~31u);  // this warp's 32 slots
+  const uint32_t lane = threadIdx.x & 31u;
   uint32_t count = *n_long;
   if (count > long_cap) count = long_cap;
-  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x) {
+  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < count; r += warps) {
     const MsmLongRun run = long_runs[r];
-    if (run.last - run.first > MSM_GIANT_SLOTS) {
-      giant_runs[atomicAdd(n_giant, 1u)] = run;  // at most `count` entries: same capacity as long_runs
-      continue;
-    }
-    XYZZ<Fq> acc = ld_words(part_pt + run.first);
-    for (uint32_t k = run.first + 1; k <= run.last; k++)
-      if (part_bkt[k] == run.bucket) g1_add(acc, ld_words(part_pt + k));
-    st_words(buckets + run.bucket, acc);
-  }
-}
-template <class Fq>
-__global__ void __launch_bounds__(128)
-msm_stitch_giant_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, const MsmLongRun* runs, const uint32_t* n_runs,
-                        XYZZ<Fq>* buckets) {
-  __shared__ uint4 sm_raw[128 * sizeof(XYZZ<Fq>) / 16];
-  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(sm_raw);
-  const uint32_t count = *n_runs;
-  for (uint32_t r = blockIdx.x; r < count; r += gridDim.x) {
-    const MsmLongRun run = runs[r];
     XYZZ<Fq> acc = XYZZ<Fq>::inf();
-    for (uint32_t k = run.first + threadIdx.x; k <= run.last; k += 128)
+    for (uint32_t k = run.first + lane; k <= run.last; k += 32)
       if (part_bkt[k] == run.bucket) g1_add(acc, ld_words(part_pt + k));
-    sm[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = 64; s >= 1; s >>= 1) {
-      if ((int)threadIdx.x < s) {
-        XYZZ<Fq> t = sm[threadIdx.x];
-        g1_add(t, sm[threadIdx.x + s]);
-        sm[threadIdx.x] = t;
+    sm[lane] = acc;
+    __syncwarp();
+    for (uint32_t s2 = 16; s2 >= 1; s2 >>= 1) {
+      if (lane < s2) {
+        XYZZ<Fq> t = sm[lane];
+        g1_add(t, sm[lane + s2]);
+        sm[lane] = t;
       }
-      __syncthreads();
+      __syncwarp();
     }
-    if (threadIdx.x == 0) st_words(buckets + run.bucket, sm[0]);
-    __syncthreads();
+    if (lane == 0) st_words(buckets + run.bucket, sm[0]);
+    __syncwarp();
   }
 }
 
@@ -310,28 +296,22 @@ msm_stitch_giant_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, const
 //     Rsum[hi] = sum_lo B[hi][lo]  (row tree),   Csum[lo] = sum_hi B[hi][lo]  (column tree),
 // and each of the two short weighted sums is done by bit planes: sum_i i V_i = sum_k 2^k sum_{i: bit k} V_i.
 
-// out[g][i] = in[g][2i] + in[g][2i+1]     (g < groups, i < len / 2)
+// Segmented sums, the building block of both trees:
+//     out[(g * nseg + s) * ni + i] = sum_{k < K} in[g * group_stride + (s * K + k) * stride_k + i * stride_i]
+// One thread per output, K serial additions each (fully inlined: a call per addition would pass two 192-byte points
+// through local memory).  Row sums take stride_k = 1 (a thread streams K consecutive buckets of its row), column sums
+// stride_k = L (consecutive threads read consecutive buckets).  A tree of pairwise kernels needs log2 launches whose tails
+// are latency-bound; K = 16 per stage gives 3 fat launches per tree with the same number of additions (+7 %).
 template <class Fq>
-__global__ void __launch_bounds__(128) msm_pair_rows_kernel(const XYZZ<Fq>* in, XYZZ<Fq>* out, size_t groups, size_t len) {
-  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  size_t half = len >> 1;
-  if (t >= groups * half) return;
-  size_t g = t / half, i = t - g * half;
-  XYZZ<Fq> a = ld_words(in + g * len + 2 * i);
-  g1_add(a, ld_words(in + g * len + 2 * i + 1));
-  st_words(out + t, a);
-}
-// out[j][h][lo] = in[j][2h][lo] + in[j][2h+1][lo]   (j < nj, h < rows / 2, lo < L)
-template <class Fq>
-__global__ void __launch_bounds__(128) msm_pair_cols_kernel(const XYZZ<Fq>* in, XYZZ<Fq>* out, size_t nj, size_t rows, size_t L) {
-  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  size_t hr = rows >> 1;
-  if (t >= nj * hr * L) return;
-  size_t lo = t % L, jh = t / L, j = jh / hr, h = jh - j * hr;
-  const XYZZ<Fq>* p = in + ((j * rows + 2 * h) * L + lo);
-  XYZZ<Fq> a = ld_words(p);
-  g1_add(a, ld_words(p + L));
-  st_words(out + t, a);
+__global__ void __launch_bounds__(128) msm_segsum_kernel(const XYZZ<Fq>* __restrict__ in, XYZZ<Fq>* __restrict__ out, size_t groups, size_t nseg,
+                                                         uint32_t K, size_t ni, size_t stride_k, size_t stride_i, size_t group_stride) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= groups * nseg * ni) return;
+  const size_t i = t % ni, gs = t / ni, sg = gs % nseg, g = gs / nseg;
+  const XYZZ<Fq>* p = in + g * group_stride + sg * K * stride_k + i * stride_i;
+  XYZZ<Fq> acc = ld_words(p);
+  for (uint32_t k = 1; k < K; k++) acc.add(ld_words(p + (size_t)k * stride_k));
+  st_words(out + t, acc);
 }
 // planes[j][p] for p in [0, nbits]: p < nbits -> sum of V[j][i] over i with bit p set; p == nbits -> sum of all.
 template <class Fq>
@@ -572,9 +552,9 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       digits[s] = DBuf<uint32_t>(cx, max_refs); hist[s] = DBuf<uint32_t>(cx, B + 1); offsets[s] = DBuf<uint32_t>(cx, B + 1);
       cursor[s] = DBuf<uint32_t>(cx, B); sorted[s] = DBuf<uint2>(cx, max_refs);
     }
-    DBuf<uint32_t> part_bkt(cx, 2 * max_threads), n_long(cx, 2);  // n_long[0]: long runs, [1]: giant runs
+    DBuf<uint32_t> part_bkt(cx, 2 * max_threads), n_long(cx, 1);  // number of queued long runs
     const uint32_t long_cap = 1u << 18;
-    DBuf<MsmLongRun> long_runs(cx, long_cap), giant_runs(cx, long_cap);
+    DBuf<MsmLongRun> long_runs(cx, long_cap);
     DBuf<XYZZ<Fq>> part_pt(cx, 2 * max_threads);
     // batched-affine levels (msm_affine.cuh): level l has at most bound[l] points
     const int LV = max_refs >= affine_min_refs ? affine_levels : 0;  // (the largest job of the batch decides the buffers)
@@ -716,12 +696,10 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       n_long.zero();
       msm_stitch_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, nthreads, q, src_off, src_ends,
                                                                            buckets.p + (size_t)j * B, long_runs.p, n_long.p, long_cap);
-      msm_stitch_long_kernel<Fq><<<2 * cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, long_runs.p, n_long.p, long_cap,
-                                                                         buckets.p + (size_t)j * B, giant_runs.p, n_long.p + 1);
-      msm_stitch_giant_kernel<Fq><<<2 * cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, giant_runs.p, n_long.p + 1,
-                                                                          buckets.p + (size_t)j * B);
+      msm_stitch_runs_kernel<Fq><<<2 * cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, long_runs.p, n_long.p, long_cap,
+                                                                         buckets.p + (size_t)j * B);
       B2M_CHECK_LAUNCH();
-      cx.launches += 3;
+      cx.launches += 2;
       cx.span_end(sp1);
       B2M_CUDA(cudaEventRecord(ev_acc[j], cx.stream));
     }
@@ -734,36 +712,38 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
   double units = 0;
   for (int j = 0; j < nj; j++) units += (double)jobs[j].n;
   size_t sp2 = cx.span_begin("msm_reduce", units);
-  DBuf<XYZZ<Fq>> ping(cx, (size_t)nj * B / 2 + 1), pong(cx, (size_t)nj * B / 4 + 1);
+  DBuf<XYZZ<Fq>> ping(cx, (size_t)nj * B / 8 + 1), pong(cx, (size_t)nj * B / 64 + 1);
   DBuf<XYZZ<Fq>> rsum(cx, (size_t)nj * R), csum(cx, (size_t)nj * L);
-  auto tree = [&](bool rows_tree) {
+  // sums over `len` summands spaced `stride_k` apart for each of `ni` positions spaced `stride_i` apart, per job:
+  // stages of K <= 16 summands per thread until one value per position is left
+  auto reduce_axis = [&](size_t len, size_t ni, size_t stride_k, size_t stride_i, XYZZ<Fq>* result) {
     const XYZZ<Fq>* cur = buckets.p;
-    size_t len = rows_tree ? L : R;  // extent being folded
+    size_t group_stride = B;
     XYZZ<Fq>* bufs[2] = {ping.p, pong.p};
     int which = 0;
-    if (len == 1) {  // nothing to fold: the sums are the buckets themselves
-      B2M_CUDA(cudaMemcpyAsync(rows_tree ? rsum.p : csum.p, cur, (size_t)nj * B * sizeof(XYZZ<Fq>), cudaMemcpyDeviceToDevice, cx.stream));
+    if (len == 1) {
+      B2M_CUDA(cudaMemcpyAsync(result, cur, (size_t)nj * B * sizeof(XYZZ<Fq>), cudaMemcpyDeviceToDevice, cx.stream));
       return;
     }
     while (len > 1) {
-      XYZZ<Fq>* out = (len == 2) ? (rows_tree ? rsum.p : csum.p) : bufs[which];
-      size_t threads;
-      if (rows_tree) {
-        threads = (size_t)nj * R * (len / 2);
-        msm_pair_rows_kernel<Fq><<<div_up(threads, 128), 128, 0, cx.stream>>>(cur, out, (size_t)nj * R, len);
-      } else {
-        threads = (size_t)nj * (len / 2) * L;
-        msm_pair_cols_kernel<Fq><<<div_up(threads, 128), 128, 0, cx.stream>>>(cur, out, (size_t)nj, len, L);
-      }
+      const uint32_t K = (uint32_t)std::min<size_t>(len, len > 16 && len < 64 ? 8 : 16);  // (keeps every stage's K >= 2)
+      const size_t nseg = len / K;
+      XYZZ<Fq>* out = nseg == 1 ? result : bufs[which];
+      const size_t threads = (size_t)nj * nseg * ni;
+      msm_segsum_kernel<Fq><<<div_up(threads, 128), 128, 0, cx.stream>>>(cur, out, (size_t)nj, nseg, K, ni, stride_k, stride_i, group_stride);
       B2M_CHECK_LAUNCH();
       cx.launches++;
+      // the stage's output is laid out [job][segment][position]: summands of a position are now `ni` apart
       cur = out;
+      group_stride = nseg * ni;
+      stride_k = ni;
+      stride_i = 1;
+      len = nseg;
       which ^= 1;
-      len >>= 1;
     }
   };
-  tree(true);
-  tree(false);
+  reduce_axis(L, R, 1, L, rsum.p);  // Rsum[hi] = sum_lo B[hi][lo]
+  reduce_axis(R, L, L, 1, csum.p);  // Csum[lo] = sum_hi B[hi][lo]
   DBuf<XYZZ<Fq>> rplanes(cx, (size_t)nj * (rbits + 1)), cplanes(cx, (size_t)nj * (cbits + 1));
   msm_bitplane_kernel<Fq><<<dim3(rbits + 1, nj), 256, 0, cx.stream>>>(rsum.p, R, rbits, rplanes.p);
   msm_bitplane_kernel<Fq><<<dim3(cbits + 1, nj), 256, 0, cx.stream>>>(csum.p, L, cbits, cplanes.p);
@@ -788,6 +768,16 @@ void Msm<Fr, Fq>::run_host(size_t base_off, const uint64_t* scalars, size_t n, u
   res.download(&h, 1);
   memcpy(out_xy, &h, sizeof(h));
   if (out_is_inf) *out_is_inf = h.is_inf() ? 1 : 0;
+}
+
+template <class Fr, class Fq>
+void Msm<Fr, Fq>::read_power(size_t i, uint64_t* out_xy) {
+  B2M_REQUIRE(i < n_srs_global, B2M_ERR_INVALID_ARG, "power %zu of %zu", i, n_srs_global);
+  B2M_REQUIRE(tab_world == 1, B2M_ERR_UNSUPPORTED, "read_power on a sharded key (the power lives on rank %zu)", i % (size_t)tab_world);
+  Affine<Fq> h;
+  B2M_CUDA(cudaMemcpyAsync(&h, tables.p + i, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->sync();
+  memcpy(out_xy, &h, sizeof(h));
 }
 
 template <class Fr, class Fq>

@@ -384,7 +384,7 @@ struct MarlinIndex : IndexBase {
   };
 
   // `PC::commit` over a round's oracles, drawing blinding polynomials from zk in the reference's order.
-  void commit_round(std::vector<Oracle*>& polys, ChaChaHost& zk) {
+  void commit_round(std::vector<Oracle*>& polys, ZkSource<b2m_rng>& zk) {
     std::vector<DBuf<Fr>> keep_sc;
     DBuf<Pt> out(cx, 2 * polys.size());
     out.zero();  // the shifted slot of an unbounded polynomial is never written
@@ -474,11 +474,12 @@ struct MarlinIndex : IndexBase {
                 n_input, n_witness, nv);
     B2M_REQUIRE(n_input == ni && is_pow2(n_input), B2M_ERR_INVALID_PUBLIC_INPUT_LEN, "formatted public input length %zu (index: %zu)",
                 n_input, ni);
-    B2M_REQUIRE(rng->kind == B2M_RNG_CHACHA8 || rng->kind == B2M_RNG_CHACHA12 || rng->kind == B2M_RNG_CHACHA20, B2M_ERR_MISSING_RNG,
-                "unsupported rng kind %d", rng->kind);
+    B2M_REQUIRE(rng->kind == B2M_RNG_CHACHA8 || rng->kind == B2M_RNG_CHACHA12 || rng->kind == B2M_RNG_CHACHA20 ||
+                    (rng->kind == B2M_RNG_CALLBACK && rng->next_u64 != nullptr),
+                B2M_ERR_MISSING_RNG, "unsupported rng kind %d", rng->kind);
     Timer tm(cx);
     size_t t_all = tm.begin("Marlin::Prover");
-    ChaChaHost zk(rng->key, rng->kind, rng->word_pos);
+    ZkSource<b2m_rng> zk(rng);
     const Fr* tw = ntt.table.tw;
     const int ml = ntt.table.max_log, lh = log_h;
     const size_t Hh = H, Xx = X, Kk = K;
@@ -864,13 +865,22 @@ struct MarlinIndex : IndexBase {
     put_compressed(proof, w_pts[1]);
     proof.push_back(0);  // gamma: no hiding polynomial is opened there
     proof.push_back(0);  // BatchLCProof.evals = None
-    rng->word_pos = zk.word_pos;
+    zk.commit_position();
     tm.end(t_all);
     timings_json = tm.json();
   }
 
-  // DensePolynomial::rand(3|H| - 1, zk_rng) on the device: attempts are 8-word slices of the stream.
-  void sample_mask(ChaChaHost& zk, Fr* out, size_t need) {
+  // DensePolynomial::rand(3|H| - 1, zk_rng): on the device when the rng is a ChaCha stream position (attempts are 8-word
+  // slices of the stream), on the host through the caller's callback otherwise (one upload).
+  void sample_mask(ZkSource<b2m_rng>& zks, Fr* out, size_t need) {
+    if (zks.callback) {
+      std::vector<Fr> h(need);
+      for (size_t i = 0; i < need; i++) h[i] = field_rand<Fr>(zks);
+      B2M_CUDA(cudaMemcpyAsync(out, h.data(), need * sizeof(Fr), cudaMemcpyHostToDevice, cx.stream));
+      cx.sync();
+      return;
+    }
+    ChaChaHost& zk = zks.cc;
     ChaChaKey key;
     memcpy(key.k, zk.key, 32);
     size_t have = 0;
@@ -920,8 +930,7 @@ void pc_commit_impl(b2m_srs* srs, Msm<Fr, Fq>& msm, int pc, size_t n_polys, cons
   bool any_hiding = false;
   for (size_t i = 0; i < n_polys; i++) any_hiding = any_hiding || hiding_bounds[i] >= 0;
   B2M_REQUIRE(!any_hiding || rng != nullptr, B2M_ERR_MISSING_RNG, "a hiding bound was requested but rng is null");
-  ChaChaHost zk;
-  if (rng) zk = ChaChaHost(rng->key, rng->kind, rng->word_pos);
+  ZkSource<b2m_rng> zk(rng);
   std::vector<DBuf<Fr>> polys, blind;
   std::vector<MsmJob<Fr, Fq>> jobs;
   DBuf<Pt> out(cx, 2 * n_polys);
@@ -974,83 +983,71 @@ void pc_commit_impl(b2m_srs* srs, Msm<Fr, Fq>& msm, int pc, size_t n_polys, cons
     memcpy(out_comm_xy + i * (2 * Fq::N / 2), &h[2 * i], sizeof(Pt));
     if (out_shifted_xy) memcpy(out_shifted_xy + i * (2 * Fq::N / 2), &h[2 * i + 1], sizeof(Pt));
   }
-  if (rng) rng->word_pos = zk.word_pos;
+  zk.commit_position();
 }
 
 // ---------------------------------------------------------------------------------------------------
 // Level 1: `PC::open_individual_opening_challenges` at one point [U ark-poly-commit marlin_pc / sonic_pc open]
 // ---------------------------------------------------------------------------------------------------
+template <class Fr>
+struct OpenItem {  // one labelled polynomial resident in HBM, with its commitment randomness
+  const Fr* dev;
+  size_t len;
+  int64_t bound;  // degree bound or -1
+  std::vector<Fr> rand, srand;  // blinding polynomials (trailing zeros stripped; empty = not hiding)
+};
+
 template <class Fr, class Fq>
-void pc_open_impl(b2m_srs* srs, Ntt<Fr>& ntt, Msm<Fr, Fq>& msm, int pc, size_t n_polys, const uint64_t* const* coeffs,
-                  const size_t* n_coeffs, const int64_t* degree_bounds, const uint64_t* rands, const uint64_t* shifted_rands,
-                  size_t rand_stride, int64_t max_degree_bound, const uint64_t* point, const uint64_t* opening_challenge,
-                  uint64_t* out_w_xy, int* out_has_random_v, uint64_t* out_random_v) {
+void pc_open_point_dev(b2m_srs* srs, Msm<Fr, Fq>& msm, int pc, const std::vector<OpenItem<Fr>>& items, int64_t max_degree_bound, const Fr& z,
+                       const Fr& xi, uint64_t* out_w_xy, int* out_has_random_v, uint64_t* out_random_v) {
   using Pt = Affine<Fq>;
   using Xy = XYZZ<Fq>;
   using M = MarlinIndex<Fr, Fq>;
   typedef typename M::HPoly HPoly;
-  (void)ntt;
   Ctx& cx = srs->ctx->cx;
   const size_t D = srs->n_g - 1;
   const bool marlin = pc == B2M_PC_MARLIN_KZG10;
-  Fr z, xi;
-  memcpy(z.l, point, sizeof(z.l));
-  memcpy(xi.l, opening_challenge, sizeof(xi.l));
   const Fr one = Fr::one();
-  auto host_poly = [&](const uint64_t* base, size_t i) {
-    HPoly h;
-    if (!base) return h;
-    for (size_t k = 0; k < rand_stride; k++) {
-      Fr c;
-      memcpy(c.l, base + 4 * (rand_stride * i + k), sizeof(c.l));
-      h.push_back(c);
-    }
-    while (!h.empty() && h.back().is_zero()) h.pop_back();
-    return h;
-  };
   size_t max_len = 1;
-  for (size_t i = 0; i < n_polys; i++) max_len = std::max(max_len, n_coeffs[i]);
-  std::vector<DBuf<Fr>> dev, keep;
+  for (auto& it : items) max_len = std::max(max_len, it.len);
+  std::vector<DBuf<Fr>> keep;
   DBuf<Fr> comb(cx, max_len), tmp(cx, max_len);
   comb.zero();
   std::vector<MsmJob<Fr, Fq>> shifted_jobs;
-  DBuf<Xy> ex(cx, n_polys + 1);
+  DBuf<Xy> ex(cx, items.size() + 1);
   int n_extra = 0;
   HPoly r, sr, srw;
   Fr ch = one;
   bool enforce = false;
-  for (size_t i = 0; i < n_polys; i++) {
-    const size_t len = n_coeffs[i];
-    B2M_REQUIRE(len <= srs->n_g, B2M_ERR_DEGREE_TOO_LARGE, "polynomial %zu has %zu coefficients, the SRS %zu powers", i, len, srs->n_g);
-    dev.emplace_back(cx, len ? len : 1);
-    if (len) dev.back().upload(reinterpret_cast<const Fr*>(coeffs[i]), len);
+  for (auto& it : items) {
+    const size_t len = it.len;
+    B2M_REQUIRE(len <= srs->n_g, B2M_ERR_DEGREE_TOO_LARGE, "a polynomial has %zu coefficients, the SRS %zu powers", len, srs->n_g);
     // comb += ch * p_i
     LcTerms<Fr> lt;
     lt.add(comb.p, max_len, one);
-    lt.add(dev.back().p, len, ch);
+    lt.add(it.dev, len, ch);
     lincomb_kernel<Fr><<<div_up(max_len, 256), 256, 0, cx.stream>>>(lt, max_len, tmp.p);
     B2M_CHECK_LAUNCH();
     cx.launches++;
     std::swap(comb, tmp);
-    M::hp_axpy(r, ch, host_poly(rands, i));
+    M::hp_axpy(r, ch, it.rand);
     ch = ch * xi;
-    if (marlin && degree_bounds[i] >= 0) {
-      B2M_REQUIRE(max_degree_bound >= degree_bounds[i] && (size_t)max_degree_bound <= D, B2M_ERR_DEGREE_TOO_LARGE, "bad degree bounds");
+    if (marlin && it.bound >= 0) {
+      B2M_REQUIRE(max_degree_bound >= it.bound && (size_t)max_degree_bound <= D, B2M_ERR_DEGREE_TOO_LARGE, "bad degree bounds");
       enforce = true;
-      HPoly srand_i = host_poly(shifted_rands, i);
       if (len > 1) {
         // shifted witness ch1 * (p_i / (X - z)) against shifted_powers: powers_of_g[D - bound ..]
         keep.emplace_back(cx, len);
-        DBuf<Fr>& s = keep.back();
-        rec_suffix<Fr>(cx, dev.back().p, s.p, len, 1, z, true);
-        Fr* ps = s.p;
+        DBuf<Fr>& sfx_i = keep.back();
+        rec_suffix<Fr>(cx, it.dev, sfx_i.p, len, 1, z, true);
+        Fr* ps = sfx_i.p;
         const Fr c1 = ch;
         ew(cx, len - 1, [=] __device__(size_t k) { st_fr(ps + 1 + k, ld_fr(ps + 1 + k) * c1); });
-        shifted_jobs.push_back(MsmJob<Fr, Fq>{s.p + 1, true, len - 1, D - (size_t)degree_bounds[i], nullptr, 0, 0, nullptr, 0, ex.p + n_extra, nullptr});
+        shifted_jobs.push_back(MsmJob<Fr, Fq>{sfx_i.p + 1, true, len - 1, D - (size_t)it.bound, nullptr, 0, 0, nullptr, 0, ex.p + n_extra, nullptr});
         n_extra++;
       }
-      M::hp_axpy(sr, ch, srand_i);
-      if (!M::hp_is_zero(srand_i)) M::hp_axpy(srw, ch, M::hp_div_linear(srand_i, z));
+      M::hp_axpy(sr, ch, it.srand);
+      if (!M::hp_is_zero(it.srand)) M::hp_axpy(srw, ch, M::hp_div_linear(it.srand, z));
       ch = ch * xi;
     }
   }
@@ -1081,6 +1078,123 @@ void pc_open_impl(b2m_srs* srs, Ntt<Fr>& ntt, Msm<Fr, Fq>& msm, int pc, size_t n
     if (marlin && enforce) rv = rv + M::hp_eval(sr, z);
   }
   memcpy(out_random_v, rv.l, sizeof(rv.l));
+}
+
+template <class Fr>
+static std::vector<Fr> host_rand_poly(const uint64_t* base, size_t rand_stride, size_t i) {
+  std::vector<Fr> h;
+  if (!base) return h;
+  for (size_t k = 0; k < rand_stride; k++) {
+    Fr c;
+    memcpy(c.l, base + 4 * (rand_stride * i + k), sizeof(c.l));
+    h.push_back(c);
+  }
+  while (!h.empty() && h.back().is_zero()) h.pop_back();
+  return h;
+}
+
+template <class Fr, class Fq>
+void pc_open_impl(b2m_srs* srs, Ntt<Fr>& ntt, Msm<Fr, Fq>& msm, int pc, size_t n_polys, const uint64_t* const* coeffs,
+                  const size_t* n_coeffs, const int64_t* degree_bounds, const uint64_t* rands, const uint64_t* shifted_rands,
+                  size_t rand_stride, int64_t max_degree_bound, const uint64_t* point, const uint64_t* opening_challenge,
+                  uint64_t* out_w_xy, int* out_has_random_v, uint64_t* out_random_v) {
+  (void)ntt;
+  Ctx& cx = srs->ctx->cx;
+  Fr z, xi;
+  memcpy(z.l, point, sizeof(z.l));
+  memcpy(xi.l, opening_challenge, sizeof(xi.l));
+  std::vector<DBuf<Fr>> dev;
+  std::vector<OpenItem<Fr>> items;
+  for (size_t i = 0; i < n_polys; i++) {
+    const size_t len = n_coeffs[i];
+    B2M_REQUIRE(len <= srs->n_g, B2M_ERR_DEGREE_TOO_LARGE, "polynomial %zu has %zu coefficients, the SRS %zu powers", i, len, srs->n_g);
+    dev.emplace_back(cx, len ? len : 1);
+    if (len) dev.back().upload(reinterpret_cast<const Fr*>(coeffs[i]), len);
+    items.push_back(OpenItem<Fr>{dev.back().p, len, degree_bounds[i], host_rand_poly<Fr>(rands, rand_stride, i),
+                                 host_rand_poly<Fr>(shifted_rands, rand_stride, i)});
+  }
+  pc_open_point_dev<Fr, Fq>(srs, msm, pc, items, max_degree_bound, z, xi, out_w_xy, out_has_random_v, out_random_v);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Level 1: `PC::open_combinations` [U ark-poly-commit marlin_pc / sonic_pc open_combinations_individual_opening_challenges]
+// ---------------------------------------------------------------------------------------------------
+template <class Fr, class Fq>
+void pc_open_combinations_impl(b2m_srs* srs, Msm<Fr, Fq>& msm, int pc, int64_t max_degree_bound, size_t n_polys, const uint64_t* const* coeffs,
+                               const size_t* n_coeffs, const int64_t* degree_bounds, const int* hiding, const uint64_t* rands,
+                               const uint64_t* shifted_rands, size_t rand_stride, size_t n_lcs, const size_t* lc_term_off, const int64_t* lc_poly,
+                               const uint64_t* lc_coeff, size_t n_queries, const size_t* query_lc, const size_t* query_point, size_t n_points,
+                               const uint64_t* points, const uint64_t* opening_challenge, uint64_t* out_w_xy, int* out_has_random_v,
+                               uint64_t* out_random_v) {
+  using M = MarlinIndex<Fr, Fq>;
+  Ctx& cx = srs->ctx->cx;
+  const bool marlin = pc == B2M_PC_MARLIN_KZG10;
+  Fr xi;
+  memcpy(xi.l, opening_challenge, sizeof(xi.l));
+  const Fr one = Fr::one();
+  std::vector<DBuf<Fr>> dev;
+  for (size_t i = 0; i < n_polys; i++) {
+    const size_t len = n_coeffs[i];
+    B2M_REQUIRE(len <= srs->n_g, B2M_ERR_DEGREE_TOO_LARGE, "polynomial %zu has %zu coefficients, the SRS %zu powers", i, len, srs->n_g);
+    dev.emplace_back(cx, len ? len : 1);
+    if (len) dev.back().upload(reinterpret_cast<const Fr*>(coeffs[i]), len);
+  }
+  // the linear-combination polynomials, their randomness and degree bound
+  std::vector<DBuf<Fr>> lc_dev;
+  std::vector<OpenItem<Fr>> lcs;
+  for (size_t l = 0; l < n_lcs; l++) {
+    const size_t t0 = lc_term_off[l], t1 = lc_term_off[l + 1];
+    size_t len = 1;
+    for (size_t t = t0; t < t1; t++)
+      if (lc_poly[t] >= 0) {
+        B2M_REQUIRE((size_t)lc_poly[t] < n_polys, B2M_ERR_INVALID_ARG, "linear combination %zu names polynomial %lld of %zu", l, (long long)lc_poly[t], n_polys);
+        len = std::max(len, n_coeffs[lc_poly[t]]);
+      }
+    lc_dev.emplace_back(cx, len);
+    lc_dev.back().zero();
+    DBuf<Fr> tmp(cx, len);
+    OpenItem<Fr> item{nullptr, len, -1, {}, {}};
+    const size_t num_terms = t1 - t0;
+    for (size_t t = t0; t < t1; t++) {
+      if (lc_poly[t] < 0) continue;  // LCTerm::One: affects the evaluation only
+      const size_t i = (size_t)lc_poly[t];
+      Fr c;
+      memcpy(c.l, lc_coeff + 4 * t, sizeof(c.l));
+      if (degree_bounds[i] >= 0) {
+        B2M_REQUIRE(num_terms == 1 && c == one, B2M_ERR_INVALID_ARG,
+                    "linear combination %zu: a degree-bounded polynomial may only appear alone with coefficient one", l);
+        item.bound = degree_bounds[i];
+      }
+      LcTerms<Fr> lt;
+      lt.add(lc_dev.back().p, len, one);
+      lt.add(dev[i].p, n_coeffs[i], c);
+      lincomb_kernel<Fr><<<div_up(len, 256), 256, 0, cx.stream>>>(lt, len, tmp.p);
+      B2M_CHECK_LAUNCH();
+      cx.launches++;
+      std::swap(lc_dev.back(), tmp);
+      if (hiding[i]) M::hp_axpy(item.rand, c, host_rand_poly<Fr>(rands, rand_stride, i));
+      if (marlin && item.bound >= 0 && hiding[i]) M::hp_axpy(item.srand, c, host_rand_poly<Fr>(shifted_rands, rand_stride, i));
+    }
+    item.dev = lc_dev.back().p;
+    lcs.push_back(std::move(item));
+  }
+  // one opening per point, the combinations queried there in label (= index) order
+  for (size_t p = 0; p < n_points; p++) {
+    std::vector<size_t> which;
+    for (size_t q = 0; q < n_queries; q++)
+      if (query_point[q] == p) {
+        B2M_REQUIRE(query_lc[q] < n_lcs, B2M_ERR_INVALID_ARG, "query %zu names linear combination %zu of %zu", q, query_lc[q], n_lcs);
+        which.push_back(query_lc[q]);
+      }
+    std::sort(which.begin(), which.end());
+    which.erase(std::unique(which.begin(), which.end()), which.end());
+    B2M_REQUIRE(!which.empty(), B2M_ERR_INVALID_ARG, "point %zu is not queried", p);
+    std::vector<OpenItem<Fr>> items;
+    for (size_t l : which) items.push_back(lcs[l]);
+    Fr z;
+    memcpy(z.l, points + 4 * p, sizeof(z.l));
+    pc_open_point_dev<Fr, Fq>(srs, msm, pc, items, max_degree_bound, z, xi, out_w_xy + p * (2 * Fq::N / 2), out_has_random_v + p, out_random_v + 4 * p);
+  }
 }
 
 }  // namespace b2m

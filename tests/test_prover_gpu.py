@@ -364,3 +364,146 @@ def test_pc_open_level1(gctx, scheme):
             assert (None if grv is None else util.fr_from_mont_limbs(curve, grv)[0]) == orv
     finally:
         srs.close()
+
+
+@pytest.mark.parametrize("scheme", list(SCHEMES))
+def test_generic_rng_callback(gctx, scheme):
+    """The rng crosses the boundary as a host callback (B2M_RNG_CALLBACK: any `RngCore`, not only ChaCha): a Level-1 commit and
+    a whole Level-2 prove driven by a callback over the oracle's generator must give the oracle's bytes and leave the generator
+    at the oracle's position -- i.e. the library issues exactly the reference's draws, in its order."""
+    curve = BLS12_381
+    f = curve.fr
+    # Level 1: commit
+    import random
+    rnd = random.Random(5)
+    D = 63
+    osrs = kzg.UniversalParams(curve, D, 0xabcdef, ec_scalar(curve, 3), 11)
+    bounds = [10, 40]
+    ck = kzg.CommitterKey(osrs, D, 1, bounds, SCHEMES[scheme])
+    polys = [kzg.LabeledPoly("a", [rnd.randrange(f.p) for _ in range(20)], None, 1), kzg.LabeledPoly("b", [rnd.randrange(f.p) for _ in range(11)], 10, 1),
+             kzg.LabeledPoly("c", [rnd.randrange(f.p) for _ in range(30)], 40, None)]
+    zk = orng.ChaChaRng(bytes(range(32)), 8)  # ChaCha8: not even one of the fast-path generators of the bench
+    ocomms, orands = kzg.commit(kzg.Engine(False), ck, polys, zk)
+    m = api.Marlin("bls12_381", scheme, ctx=gctx)
+    gidx = sorted({0, 1, 2} | ({D - d + i for d in bounds for i in range(3)} if scheme == "sonic_kzg10" else set()))
+    srs = m.srs_from_points(util.points_to_limbs(curve, osrs.powers_of_g), util.points_to_limbs(curve, [osrs.power_of_gamma_g(i) for i in gidx]), gidx)
+    try:
+        src = orng.ChaChaRng(bytes(range(32)), 8)
+        comm, shifted, rand, srand = m.commit(srs, [(util.fr_to_mont_limbs(curve, p.coeffs), p.degree_bound, p.hiding_bound) for p in polys],
+                                              api.CallbackRng(src.next_u64))
+        assert src.word_pos == zk.word_pos
+        assert util.points_from_limbs(curve, comm) == [c.comm for c in ocomms]
+        for i, r in enumerate(orands):
+            assert util.fr_from_mont_limbs(curve, rand[i])[:len(r.rand)] == r.rand
+    finally:
+        srs.close()
+    # Level 2: prove (the mask polynomial is then drawn on the host through the callback)
+    n = 64
+    rng = orng.test_rng()
+    a, b = orng.field_rand(f, rng), orng.field_rand(f, rng)
+    ocirc = or1cs.dummy_circuit(f, a, b, 10, n)
+    osrs = omarlin.universal_setup(curve, n, n, 3 * n, beta=0x1234567, g_scalar=1, gamma=7)
+    eng = kzg.Engine(use_trapdoor=True)
+    opk = omarlin.index(osrs, ocirc, SCHEMES[scheme], eng)
+    zk = orng.ChaChaRng(bytes(range(1, 33)), 20)
+    want = omarlin.serialize_proof(curve, SCHEMES[scheme], omarlin.prove(opk, ocirc, zk, eng))
+    srs = m.srs_from_trapdoor(osrs.max_degree, beta=0x1234567, gamma=7, degree_bounds=(n - 2, 4 * n - 2))
+    try:
+        gcirc = gr1cs.dummy_circuit(0, a, b, 10, n)
+        pk = m.index(srs, gcirc)
+        try:
+            src = orng.ChaChaRng(bytes(range(1, 33)), 20)
+            assert m.prove(pk, gcirc, api.CallbackRng(src.next_u64)) == want
+            assert src.word_pos == zk.word_pos
+        finally:
+            pk.close()
+    finally:
+        srs.close()
+
+
+@pytest.mark.parametrize("scheme", list(SCHEMES))
+def test_trim_and_open_combinations_level1(gctx, scheme):
+    """`PC::trim` + `PC::commit(ck, ..)` + `PC::open_combinations` through the C ABI (b2m_trim, b2m_ck_commit,
+    b2m_ck_open_combinations) against the oracle's restatement: same BatchLCProof (w, random_v per point, points in label order),
+    the committer key's checks (unsupported bound, degree above the supported one), the MarlinKZG10 shift powers."""
+    import random
+    from marlin_b200 import _lib
+    curve = BLS12_381
+    f = curve.fr
+    p = f.p
+    rnd = random.Random(99)
+    D = 63
+    osrs = kzg.UniversalParams(curve, D, 0xabcdef, ec_scalar(curve, 3), 11)
+    bounds = [10, 40]
+    ock = kzg.CommitterKey(osrs, D, 1, bounds, SCHEMES[scheme])
+    polys = [kzg.LabeledPoly("a", [rnd.randrange(p) for _ in range(20)], None, 1), kzg.LabeledPoly("b", [rnd.randrange(p) for _ in range(11)], 10, 1),
+             kzg.LabeledPoly("c", [rnd.randrange(p) for _ in range(33)], 40, None), kzg.LabeledPoly("d", [rnd.randrange(p) for _ in range(64)], None, None),
+             kzg.LabeledPoly("e", [rnd.randrange(p) for _ in range(7)], None, 1)]
+    zk = orng.ChaChaRng(bytes(range(32)), 12)
+    eng = kzg.Engine(False)
+    _, orands = kzg.commit(eng, ock, polys, zk)
+    k1, k2, k3 = rnd.randrange(p), rnd.randrange(p), rnd.randrange(p)
+    # labels sort as: "b" < "c" < "lc_mixed" < "lc_two": single bounded polynomials, a hiding mix with a constant term, a non-hiding pair
+    lcs = [kzg.LinearCombination("b", [(1, "b")]), kzg.LinearCombination("c", [(1, "c")]),
+           kzg.LinearCombination("lc_mixed", [(k1, "a"), (k2, "d"), (5, None), (k3, "e")]), kzg.LinearCombination("lc_two", [(k2, "d"), (k1, "d")])]
+    z_beta, z_gamma, xi = rnd.randrange(p), rnd.randrange(p), rnd.randrange(1 << 128)
+    qs = [("b", ("beta", z_beta)), ("lc_mixed", ("beta", z_beta)), ("lc_two", ("gamma", z_gamma)), ("c", ("gamma", z_gamma)), ("lc_mixed", ("gamma", z_gamma))]
+    want = kzg.open_combinations(eng, ock, lcs, polys, orands, qs, xi)
+    m = api.Marlin("bls12_381", scheme, ctx=gctx)
+    gidx = sorted({0, 1, 2} | ({D - d + i for d in bounds for i in range(3)} if scheme == "sonic_kzg10" else set()))
+    srs = m.srs_from_points(util.points_to_limbs(curve, osrs.powers_of_g), util.points_to_limbs(curve, [osrs.power_of_gamma_g(i) for i in gidx]), gidx)
+    try:
+        ck = m.trim(srs, D, 1, bounds)
+        try:
+            gp = [(util.fr_to_mont_limbs(curve, q.coeffs), q.degree_bound, q.hiding_bound) for q in polys]
+            comm, shifted, rand, srand = m.commit(ck, gp, api.ZkRng(bytes(range(32)), 12))
+            label_idx = {q.label: i for i, q in enumerate(polys)}
+            lc_idx = {lc.label: i for i, lc in enumerate(lcs)}
+            glcs = [[(util.fr_to_mont_limbs(curve, [c])[0], None if t is None else label_idx[t]) for c, t in lc.terms] for lc in lcs]
+            gqs = [(lc_idx[l], 0 if pl == "beta" else 1) for l, (pl, _) in qs]
+            got = m.open_combinations(ck, gp, rand, srand, glcs, gqs, util.fr_to_mont_limbs(curve, [z_beta, z_gamma]), util.fr_to_mont_limbs(curve, [xi])[0])
+            assert len(got) == len(want) == 2
+            for (gw, grv), (ow, orv) in zip(got, want):
+                assert util.points_from_limbs(curve, gw)[0] == ow
+                assert (None if grv is None else util.fr_from_mont_limbs(curve, grv)[0]) == orv
+            if scheme == "marlin_kzg10":
+                for d in bounds:
+                    assert util.points_from_limbs(curve, ck.shift_power(d))[0] == osrs.powers_of_g[D - d]
+            # the committer key's checks [U ark-poly-commit check_degrees_and_bounds / Error::*]
+            with pytest.raises(_lib.B2MError) as e:
+                m.commit(ck, [(util.fr_to_mont_limbs(curve, [1, 2, 3]), 12, None)], None)  # 12 is not an enforced bound
+            assert e.value.code == 1
+            with pytest.raises(_lib.B2MError) as e:
+                m.open_combinations(ck, gp, rand, srand, [[(util.fr_to_mont_limbs(curve, [2])[0], 1)]], [(0, 0)], util.fr_to_mont_limbs(curve, [z_beta]),
+                                    util.fr_to_mont_limbs(curve, [xi])[0])  # a bounded polynomial scaled by 2: EquationHasDegreeBounds
+            assert e.value.code == 1
+        finally:
+            ck.close()
+        small = m.trim(srs, 16, 1, [10])
+        try:
+            with pytest.raises(_lib.B2MError) as e:
+                m.commit(small, [(util.fr_to_mont_limbs(curve, list(range(1, 19))), None, None)], None)  # degree 17 > supported 16
+            assert e.value.code == 6
+        finally:
+            small.close()
+        with pytest.raises(_lib.B2MError) as e:
+            m.trim(srs, D + 1, 1, [])  # TrimmingDegreeTooLarge
+        assert e.value.code == 6
+    finally:
+        srs.close()
+
+
+def test_destroy_order_is_free(b2m_ctx):
+    """Handles may be destroyed in any order: a parent destroyed first is only marked and goes with its last child."""
+    curve = BLS12_381
+    m = api.Marlin("bls12_381", "marlin_kzg10", device=0)  # its own context, destroyed FIRST
+    srs = m.srs_from_trapdoor(63, beta=5)
+    circ = gr1cs.dummy_circuit(0, 3, 4, 10, 16)
+    pk = m.index(srs, circ)
+    ck = m.trim(srs, 63, 1, [10])
+    m.ctx.close()
+    srs.close()
+    proof = m.prove(pk, circ, api.ZkRng.test_rng())  # the index still works: its SRS and context are alive underneath
+    assert len(proof) > 800
+    ck.close()
+    pk.close()
