@@ -111,10 +111,15 @@ int b2m_srs_affine_levels(const b2m_srs* srs);
 /* MSM over the slice powers_of_g[base_off .. base_off+n) with canonical host scalars. */
 int b2m_srs_msm(b2m_srs* srs, size_t base_off, const uint64_t* scalars, size_t n, uint64_t* out_xy,
                 int* out_is_inf);
-/* Test-SRS generator (replaces the G1 half of `KZG10::setup`, [U ark-poly-commit kzg10]):
- * fills powers_of_g[i] = beta^i * g for i < n on the GPU.  beta is a canonical Fr. */
+/* SRS generation, the G1 half of `KZG10::setup` (reference src/lib.rs:79-96 -> [U ark-poly-commit kzg10::setup]):
+ * b2m_g1_powers fills powers_of_g[i] = beta^i * g for i < n; b2m_fixed_base_msm is the general
+ * `FixedBaseMSM::multi_scalar_mul(.., g, scalars)` [U ark-ec msm/fixed_base.rs] (out[i] = scalars[i] * g, e.g. the
+ * powers_of_gamma_g at arbitrary exponents).  Both: one 8-bit window table of g, <= 32 mixed additions per scalar, batch
+ * normalisation to affine.  beta and scalars are canonical Fr. */
 int b2m_g1_powers(b2m_ctx* ctx, int curve, const uint64_t* g_xy, const uint64_t* beta, size_t n,
                   uint64_t* out_powers_xy);
+int b2m_fixed_base_msm(b2m_ctx* ctx, int curve, const uint64_t* g_xy, const uint64_t* scalars, size_t n,
+                       uint64_t* out_xy);
 
 /* The caller's `zk_rng: &mut R` / `rng: Option<&mut dyn RngCore>` (reference src/lib.rs:154,125).  Two forms:
  *  - kind = B2M_RNG_CHACHA8/12/20, the fast path for the generators the reference's tests and benches use

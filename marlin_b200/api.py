@@ -187,12 +187,12 @@ class Marlin:
         for d in sorted(set(degree_bounds)):
             idx += [md - d + i for i in range(3) if md - d + i <= md]
         idx = sorted(set(idx))
+        # powers_of_gamma_g at the needed exponents: FixedBaseMSM(gamma_g, [beta^i]) with gamma_g = gamma * g
+        gamma_g = np.zeros((1, 2 * lq), dtype=np.uint64)
+        _lib.check(L.b2m_fixed_base_msm(self.ctx.handle, cid, _lib.ptr(g_l), _lib.ptr(_lib.ints_to_limbs([gamma % r], 4)), 1, _lib.ptr(gamma_g)))
+        exps = _lib.ints_to_limbs([pow(beta % r, i, r) for i in idx], 4)
         gam = np.zeros((len(idx), 2 * lq), dtype=np.uint64)
-        gamma_l = _lib.ints_to_limbs([gamma % r], 4)
-        inf = ctypes.c_int(0)
-        for k, i in enumerate(idx):
-            base = np.ascontiguousarray(powers[i:i + 1])
-            _lib.check(L.b2m_msm_g1(self.ctx.handle, cid, _lib.ptr(base), _lib.ptr(gamma_l), 1, _lib.ptr(gam[k]), ctypes.byref(inf)))
+        _lib.check(L.b2m_fixed_base_msm(self.ctx.handle, cid, _lib.ptr(gamma_g), _lib.ptr(exps), len(idx), _lib.ptr(gam)))
         return self.srs_from_points(powers, gam, idx, window_bits)
 
     def srs_from_points(self, powers_limbs, gamma_limbs, gamma_indices, window_bits=0):

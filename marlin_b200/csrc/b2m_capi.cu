@@ -160,6 +160,16 @@ int b2m_g1_powers(b2m_ctx* ctx, int curve, const uint64_t* g_xy, const uint64_t*
   });
 }
 
+int b2m_fixed_base_msm(b2m_ctx* ctx, int curve, const uint64_t* g_xy, const uint64_t* scalars, size_t n, uint64_t* out_xy) {
+  return guard([&] {
+    B2M_REQUIRE(ctx && g_xy && (scalars || n == 0) && (out_xy || n == 0), B2M_ERR_INVALID_ARG, "null argument");
+    ctx->cx.use();
+    if (curve == B2M_CURVE_BLS12_381) Msm<FrBls, FqBls>::fixed_base_host(ctx->cx, g_xy, scalars, nullptr, 0, n, out_xy);
+    else if (curve == B2M_CURVE_BN254) Msm<FrBn, FqBn>::fixed_base_host(ctx->cx, g_xy, scalars, nullptr, 0, n, out_xy);
+    else throw Error(B2M_ERR_INVALID_ARG, "unknown curve id");
+  });
+}
+
 // ---- Level 1 ----------------------------------------------------------------------------------
 int b2m_pc_commit(b2m_srs* srs, int pc_variant, size_t n_polys, const uint64_t* const* coeffs, const size_t* n_coeffs,
                   const int64_t* degree_bounds, const int64_t* hiding_bounds, b2m_rng* rng, uint64_t* out_comm_xy,

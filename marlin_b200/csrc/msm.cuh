@@ -84,6 +84,9 @@ struct Msm {
   // powers_of_g[i] (affine Montgomery limbs) back to the host: window-0 table entry, from the GPU that holds it
   void read_power(size_t i, uint64_t* out_xy);
   static void g1_powers_host(Ctx& cx, const uint64_t* g_xy, const uint64_t* beta, size_t n, uint64_t* out);
+  // out[i] = scalars[i] * g (canonical host scalars), or beta^(first + i) * g when scalars is null: windowed fixed-base
+  // multiplication + batch normalisation [U ark-ec FixedBaseMSM::multi_scalar_mul as KZG10::setup uses it]
+  static void fixed_base_host(Ctx& cx, const uint64_t* g_xy, const uint64_t* scalars, const uint64_t* beta, size_t first, size_t n, uint64_t* out);
 };
 
 }  // namespace b2m

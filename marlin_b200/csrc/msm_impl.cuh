@@ -217,11 +217,14 @@ __global__ void __launch_bounds__(128, MINB) msm_affine_level_sp_kernel(const Af
 // msm_stitch_runs_kernel, which reduces it with a whole warp.
 struct MsmLongRun {
   uint32_t first, last, bucket;  // partial slots [first, last]
+  uint32_t dst;                  // MSM_NO_DIGIT: the run's sum is the bucket; else: chunk-partial slot it goes to
 };
+constexpr uint32_t MSM_RUN_CHUNK = 256;  // slots one warp folds; longer runs are cut into chunks + one second-stage entry
 template <class Fq>
 __global__ void __launch_bounds__(128)
 msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nthreads, const uint32_t q, const uint32_t* offsets,
-                  const uint32_t* ends, XYZZ<Fq>* buckets, MsmLongRun* long_runs, uint32_t* n_long, uint32_t long_cap) {
+                  const uint32_t* ends, XYZZ<Fq>* buckets, MsmLongRun* long_runs, MsmLongRun* final_runs, uint32_t* n_long, uint32_t long_cap,
+                  uint32_t chunk_cap) {
   // One thread per accumulate-thread u.  A run of partials starts either in u's tail slot (a bucket that
   // begins inside u's range and continues into u + 1) or in u's head slot when the bucket begins exactly at
   // u's first reference; u can hold only one of the two.  The common run is the pair (tail of u, head of
@@ -238,12 +241,30 @@ msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nthr
   const uint32_t t1 = (ends[b] - 1u) / q;  // thread holding the bucket's last reference
   const uint32_t last = 2u * t1;                          // its head slot closes the run
   if (t1 > (uint32_t)u + 1u) {
-    uint32_t slot = atomicAdd(n_long, 1u);
-    if (slot < long_cap) {
-      long_runs[slot] = MsmLongRun{first, last, b};
-      return;
+    // n_long[0]: queued (first-stage) entries, [1]: second-stage entries, [2]: chunk-partial slots handed out
+    const uint32_t nslots = last - first + 1u;
+    if (nslots <= MSM_RUN_CHUNK) {
+      const uint32_t slot = atomicAdd(n_long, 1u);
+      if (slot < long_cap) {
+        long_runs[slot] = MsmLongRun{first, last, b, MSM_NO_DIGIT};
+        return;
+      }
+    } else {
+      const uint32_t nch = (nslots + MSM_RUN_CHUNK - 1u) / MSM_RUN_CHUNK;
+      const uint32_t c0 = atomicAdd(n_long + 2, nch);
+      const uint32_t base = atomicAdd(n_long, nch);
+      if (c0 + nch <= chunk_cap && base + nch <= long_cap) {
+        for (uint32_t k = 0; k < nch; k++) {
+          const uint32_t f = first + k * MSM_RUN_CHUNK;
+          const uint32_t l = (last - f >= MSM_RUN_CHUNK) ? f + MSM_RUN_CHUNK - 1u : last;
+          long_runs[base + k] = MsmLongRun{f, l, b, c0 + k};
+        }
+        final_runs[atomicAdd(n_long + 1, 1u)] = MsmLongRun{c0, c0 + nch - 1u, b, MSM_NO_DIGIT};  // (at most chunk_cap entries)
+        return;
+      }
+      for (uint32_t k = 0; k < nch && base + k < long_cap; k++) long_runs[base + k] = MsmLongRun{1u, 0u, b, MSM_NO_DIGIT};  // empty entries
     }
-    XYZZ<Fq> acc = ld_words(part_pt + first);  // overflow of the queue: fold serially
+    XYZZ<Fq> acc = ld_words(part_pt + first);  // overflow of a queue: fold serially
     for (uint32_t k = first + 1; k <= last; k++)
       if (part_bkt[k] == b) g1_add(acc, ld_words(part_pt + k));
     st_words(buckets + b, acc);
@@ -254,25 +275,29 @@ msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nthr
   st_words(buckets + b, acc);
 }
 // Runs longer than a pair (heavy buckets: with a short top window -- e.g. 3 bits at c = 18, which is what an 8-GPU
-// shard of a 2^20 key picks -- ALL references of that window land in a handful of buckets, each cut into hundreds of
-// partials).  One WARP per queued run: the lanes stride over the run's slots, then a 5-step tree through shared
-// memory.  (Round 1 folded runs of up to 256 slots serially in one thread: 256 dependent XYZZ additions, ~2 ms of
-// latency per MSM, the reason `msm_stitch` grew from 1.3 ms to 8-13 ms per proof on 4 and 8 GPUs.)
-template <class Fq>
+// shard of a 2^20 key picks -- ALL references of that window land in eight buckets of n / 8 references, each cut into
+// thousands of partials).  One WARP per queued entry: the lanes stride over the entry's slots, then a 5-step tree through
+// shared memory; runs of more than MSM_RUN_CHUNK slots were queued as chunks whose sums a second launch (FINAL) adds up.
+// (Round 1 folded runs of up to 256 slots serially in one thread -- 256 dependent XYZZ additions, ~2 ms of latency per
+// MSM -- and longer ones in one block each: `msm_stitch` grew from 1.3 ms to 8-13 ms per proof on 4 and 8 GPUs.)
+template <class Fq, bool FINAL>
 __global__ void __launch_bounds__(128)
-msm_stitch_runs_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, const MsmLongRun* long_runs, const uint32_t* n_long,
-                       uint32_t long_cap, XYZZ<Fq>* buckets) {
+msm_stitch_runs_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, const MsmLongRun* runs, const uint32_t* n_runs, uint32_t cap,
+                       XYZZ<Fq>* buckets, XYZZ<Fq>* chunk_pt) {
   __shared__ uint4 sm_raw[128 * sizeof(XYZZ<Fq>) / 16];
   XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(sm_raw) + (threadIdx.x & ~31u);  // this warp's 32 slots
   const uint32_t lane = threadIdx.x & 31u;
-  uint32_t count = *n_long;
-  if (count > long_cap) count = long_cap;
+  uint32_t count = *n_runs;
+  if (count > cap) count = cap;
   const uint32_t warps = gridDim.x * (blockDim.x >> 5);
   for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < count; r += warps) {
-    const MsmLongRun run = long_runs[r];
+    const MsmLongRun run = runs[r];
+    if (run.first > run.last) continue;  // (placeholder left by an overflowing queue)
     XYZZ<Fq> acc = XYZZ<Fq>::inf();
-    for (uint32_t k = run.first + lane; k <= run.last; k += 32)
-      if (part_bkt[k] == run.bucket) g1_add(acc, ld_words(part_pt + k));
+    for (uint32_t k = run.first + lane; k <= run.last; k += 32) {
+      if (FINAL) g1_add(acc, ld_words(chunk_pt + k));
+      else if (part_bkt[k] == run.bucket) g1_add(acc, ld_words(part_pt + k));
+    }
     sm[lane] = acc;
     __syncwarp();
     for (uint32_t s2 = 16; s2 >= 1; s2 >>= 1) {
@@ -283,7 +308,7 @@ msm_stitch_runs_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, const 
       }
       __syncwarp();
     }
-    if (lane == 0) st_words(buckets + run.bucket, sm[0]);
+    if (lane == 0) st_words(run.dst == MSM_NO_DIGIT ? buckets + run.bucket : chunk_pt + run.dst, sm[0]);
     __syncwarp();
   }
 }
@@ -394,13 +419,60 @@ __global__ void __launch_bounds__(32) msm_combine_kernel(const XYZZ<Fq>* all, in
   if (jobs.j[j].out_affine) st_words(reinterpret_cast<Affine<Fq>*>(jobs.j[j].out_affine), g1_to_affine(total));
 }
 
-// out[i] = beta^i * g  (test-SRS generation; the G1 half of KZG10::setup)
+// ---- fixed-base scalar multiplication (`KZG10::setup`: powers_of_g, powers_of_gamma_g) ---------------------------------
+// [U ark-ec FixedBaseMSM::get_window_table / multi_scalar_mul]: one table of j * 2^(8 k) * g (32 windows x 255 multiples,
+// 786 KB: L2-resident), then every scalar costs at most 32 mixed additions instead of a 255-step double-and-add; the results
+// are normalised together (Montgomery's trick over FB_NORM points per thread: `ProjectiveCurve::batch_normalization`).
+constexpr int FB_WIN = 8, FB_WINDOWS = 32, FB_NORM = 16;
+template <class Fq>
+__global__ void fixed_base_table_kernel(Affine<Fq> g, Affine<Fq>* table) {  // table[k * 256 + j] = j * 2^(8 k) * g  (j = 0: infinity)
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= FB_WINDOWS * 256) return;
+  const int k = t >> 8, j = t & 255;
+  uint32_t sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  sc[k >> 2] = (uint32_t)j << (8 * (k & 3));
+  st_words(table + t, j ? g1_to_affine(g1_scalar_mul<Fq>(g, sc, 8)) : Affine<Fq>::inf());
+}
+// out[i] = scalar_i * g with scalar_i = scalars[i] (canonical), or beta^(first + i) when scalars == nullptr
 template <class Fr, class Fq>
-__global__ void g1_powers_kernel(Affine<Fq> g, Fr beta, size_t n, Affine<Fq>* out) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) fixed_base_mul_kernel(const Affine<Fq>* __restrict__ table, const Fr* scalars, Fr beta, size_t first, size_t n,
+                                                             XYZZ<Fq>* out) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Fr k = beta.pow_u64(i).to_canonical();
-  st_words(out + i, g1_to_affine(g1_scalar_mul<Fq>(g, k.l, Fr::N)));
+  const Fr k = scalars ? ld_fr(scalars + i) : beta.pow_u64(first + i).to_canonical();
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+  for (int w = 0; w < FB_WINDOWS && w * FB_WIN < 32 * Fr::N; w++) {
+    const uint32_t d = (k.l[w >> 2] >> (8 * (w & 3))) & 255u;
+    if (d) g1_add_mixed(acc, ld_affine(table + w * 256 + d));
+  }
+  st_words(out + i, acc);
+}
+// pts[i] (XYZZ) -> affine: x = X / ZZ, y = Y / ZZZ with one inversion per FB_NORM points
+template <class Fq>
+__global__ void __launch_bounds__(128) batch_normalize_kernel(const XYZZ<Fq>* pts, size_t n, Affine<Fq>* out) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t i0 = t * FB_NORM;
+  if (i0 >= n) return;
+  const int cnt = (int)(n - i0 < (size_t)FB_NORM ? n - i0 : FB_NORM);
+  Fq pref[FB_NORM];
+  Fq run = Fq::one();
+  for (int k = 0; k < cnt; k++) {
+    const Fq zzz = ld_words(&pts[i0 + k].ZZZ);
+    pref[k] = run;
+    if (!zzz.is_zero()) run = run * zzz;  // (infinity stays out of the product)
+  }
+  Fq inv = fq_inverse(run);
+  for (int k = cnt - 1; k >= 0; k--) {
+    const XYZZ<Fq> p = ld_words(pts + i0 + k);
+    if (p.is_inf()) {
+      st_words(out + i0 + k, Affine<Fq>::inf());
+      continue;
+    }
+    const Fq izzz = inv * pref[k];
+    inv = inv * p.ZZZ;
+    const Fq izz = (p.ZZ * izzz).sqr();
+    st_words(out + i0 + k, Affine<Fq>{p.X * izz, p.Y * izzz});
+  }
 }
 
 // ---- host driver ------------------------------------------------------------------------------
@@ -413,6 +485,19 @@ int Msm<Fr, Fq>::pick_window(size_t n) {
   int c = lg - 1;
   if (c < MSM_MIN_WINDOW) c = MSM_MIN_WINDOW;
   if (c > 20) c = 20;
+  // The top window only holds what is left of the scalar: (BITS + 1) - (W - 1) c bits.  When that is a handful of bits
+  // (c = 18: 4, c = 17: 1) EVERY scalar sends its top-window reference to one of a few buckets -- eight buckets of n / 8
+  // references each at c = 18 -- which the balanced accumulation then cuts into thousands of partials.  Step to the
+  // nearest width whose top window is reasonably full.
+  auto top_bits = [](int w) {
+    const int W = (Fr::Params::BITS + 1 + w - 1) / w;
+    return Fr::Params::BITS + 1 - (W - 1) * w;
+  };
+  if (top_bits(c) < 6) {
+    if (c + 1 <= 20 && top_bits(c + 1) >= 6) c = c + 1;
+    else if (c - 1 >= MSM_MIN_WINDOW && top_bits(c - 1) >= 6) c = c - 1;
+    else if (c - 2 >= MSM_MIN_WINDOW && top_bits(c - 2) >= 6) c = c - 2;
+  }
   return c;
 }
 
@@ -552,9 +637,11 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       digits[s] = DBuf<uint32_t>(cx, max_refs); hist[s] = DBuf<uint32_t>(cx, B + 1); offsets[s] = DBuf<uint32_t>(cx, B + 1);
       cursor[s] = DBuf<uint32_t>(cx, B); sorted[s] = DBuf<uint2>(cx, max_refs);
     }
-    DBuf<uint32_t> part_bkt(cx, 2 * max_threads), n_long(cx, 1);  // number of queued long runs
+    DBuf<uint32_t> part_bkt(cx, 2 * max_threads), n_long(cx, 3);  // queued long-run entries, second-stage entries, chunk slots
     const uint32_t long_cap = 1u << 18;
-    DBuf<MsmLongRun> long_runs(cx, long_cap);
+    const uint32_t chunk_cap = (uint32_t)(4 * max_threads / MSM_RUN_CHUNK + 4);  // every chunk but a run's last covers MSM_RUN_CHUNK slots
+    DBuf<MsmLongRun> long_runs(cx, long_cap), final_runs(cx, chunk_cap);
+    DBuf<XYZZ<Fq>> chunk_pt(cx, chunk_cap);
     DBuf<XYZZ<Fq>> part_pt(cx, 2 * max_threads);
     // batched-affine levels (msm_affine.cuh): level l has at most bound[l] points
     const int LV = max_refs >= affine_min_refs ? affine_levels : 0;  // (the largest job of the batch decides the buffers)
@@ -695,11 +782,14 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       size_t sp1 = cx.span_begin("msm_stitch", (double)n);
       n_long.zero();
       msm_stitch_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, nthreads, q, src_off, src_ends,
-                                                                           buckets.p + (size_t)j * B, long_runs.p, n_long.p, long_cap);
-      msm_stitch_runs_kernel<Fq><<<2 * cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, long_runs.p, n_long.p, long_cap,
-                                                                         buckets.p + (size_t)j * B);
+                                                                           buckets.p + (size_t)j * B, long_runs.p, final_runs.p, n_long.p, long_cap,
+                                                                           chunk_cap);
+      msm_stitch_runs_kernel<Fq, false><<<4 * cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, long_runs.p, n_long.p, long_cap,
+                                                                                buckets.p + (size_t)j * B, chunk_pt.p);
+      msm_stitch_runs_kernel<Fq, true><<<cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, final_runs.p, n_long.p + 1, chunk_cap,
+                                                                           buckets.p + (size_t)j * B, chunk_pt.p);
       B2M_CHECK_LAUNCH();
-      cx.launches += 2;
+      cx.launches += 3;
       cx.span_end(sp1);
       B2M_CUDA(cudaEventRecord(ev_acc[j], cx.stream));
     }
@@ -781,19 +871,39 @@ void Msm<Fr, Fq>::read_power(size_t i, uint64_t* out_xy) {
 }
 
 template <class Fr, class Fq>
-void Msm<Fr, Fq>::g1_powers_host(Ctx& cx, const uint64_t* g_xy, const uint64_t* beta, size_t n, uint64_t* out) {
+void Msm<Fr, Fq>::fixed_base_host(Ctx& cx, const uint64_t* g_xy, const uint64_t* scalars, const uint64_t* beta, size_t first, size_t n, uint64_t* out) {
   Affine<Fq> g;
   memcpy(&g, g_xy, sizeof(g));
-  Fr b;
-  memcpy(&b, beta, sizeof(b));
-  b = Fr::from_canonical(b);
-  DBuf<Affine<Fq>> d(cx, n ? n : 1);
-  if (n) {
-    g1_powers_kernel<Fr, Fq><<<div_up(n, 64), 64, 0, cx.stream>>>(g, b, n, d.p);
-    B2M_CHECK_LAUNCH();
-    cx.launches++;
-    d.download(reinterpret_cast<Affine<Fq>*>(out), n);
+  Fr b = Fr::zero();
+  if (beta) {
+    memcpy(&b, beta, sizeof(b));
+    b = Fr::from_canonical(b);
   }
+  if (n == 0) return;
+  DBuf<Affine<Fq>> table(cx, FB_WINDOWS * 256);
+  fixed_base_table_kernel<Fq><<<div_up(FB_WINDOWS * 256, 64), 64, 0, cx.stream>>>(g, table.p);
+  B2M_CHECK_LAUNCH();
+  cx.launches++;
+  // in slices, so that a 2^26-power key needs neither 13 GB of XYZZ scratch nor one giant staging copy
+  const size_t slice = (size_t)1 << 22;
+  DBuf<XYZZ<Fq>> acc(cx, std::min(n, slice));
+  DBuf<Affine<Fq>> aff(cx, std::min(n, slice));
+  DBuf<Fr> sc;
+  if (scalars) sc = DBuf<Fr>(cx, std::min(n, slice));
+  for (size_t at = 0; at < n; at += slice) {
+    const size_t m = std::min(slice, n - at);
+    if (scalars) sc.upload(reinterpret_cast<const Fr*>(scalars) + at, m);
+    fixed_base_mul_kernel<Fr, Fq><<<div_up(m, 128), 128, 0, cx.stream>>>(table.p, scalars ? sc.p : nullptr, b, first + at, m, acc.p);
+    batch_normalize_kernel<Fq><<<div_up(div_up(m, FB_NORM), 128), 128, 0, cx.stream>>>(acc.p, m, aff.p);
+    B2M_CHECK_LAUNCH();
+    cx.launches += 2;
+    aff.download(reinterpret_cast<Affine<Fq>*>(out) + at, m);
+  }
+}
+
+template <class Fr, class Fq>
+void Msm<Fr, Fq>::g1_powers_host(Ctx& cx, const uint64_t* g_xy, const uint64_t* beta, size_t n, uint64_t* out) {
+  fixed_base_host(cx, g_xy, nullptr, beta, 0, n, out);
 }
 
 }  // namespace b2m

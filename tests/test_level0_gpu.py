@@ -85,6 +85,26 @@ def test_g1_powers_matches_oracle(b2m_ctx, curve):
 
 
 @pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
+def test_fixed_base_msm_matches_oracle(b2m_ctx, curve):
+    """b2m_fixed_base_msm (`FixedBaseMSM::multi_scalar_mul` of KZG10::setup): scalars with zero bytes / zero / r - 1 / one, a base
+    other than the generator, and more points than one normalisation batch; and b2m_g1_powers across a batch boundary."""
+    import ctypes
+    rnd = random.Random(77)
+    r = curve.fr.p
+    base = ec.scalar_mul(curve, 0xabcdef12345, curve.g)
+    sc = [0, 1, 2, r - 1, 1 << 200, (1 << 64) + 255, 0xff00ff00ff00] + [rnd.randrange(r) for _ in range(30)]
+    out = np.zeros((len(sc), 2 * curve.fq.limbs64), dtype=np.uint64)
+    _lib.check(_lib.lib().b2m_fixed_base_msm(b2m_ctx, util.CURVE_ID[curve.name], _lib.ptr(util.points_to_limbs(curve, [base])),
+                                             _lib.ptr(util.fr_to_canon_limbs(curve, sc)), len(sc), _lib.ptr(out)))
+    assert util.points_from_limbs(curve, out) == [ec.scalar_mul(curve, k, base) if k else None for k in sc]
+    beta = 0x5eed5eed5eed5eed5eed5eed % r
+    n = 1000
+    got = util.points_from_limbs(curve, util.gpu_powers(b2m_ctx, curve, curve.g, beta, n))
+    for i in (0, 1, 15, 16, 17, 255, 256, 999):
+        assert got[i] == ec.scalar_mul(curve, pow(beta, i, r), curve.g), i
+
+
+@pytest.mark.parametrize("curve", CURVES, ids=lambda c: c.name)
 @pytest.mark.parametrize("window_bits", [0, 8, 11])
 def test_msm_small_sizes_match_oracle(b2m_ctx, curve, window_bits):
     rnd = random.Random(7)
