@@ -121,6 +121,20 @@ int b2m_g1_powers(b2m_ctx* ctx, int curve, const uint64_t* g_xy, const uint64_t*
 int b2m_fixed_base_msm(b2m_ctx* ctx, int curve, const uint64_t* g_xy, const uint64_t* scalars, size_t n,
                        uint64_t* out_xy);
 
+/* G2 half of `KZG10::setup` [U ark-poly-commit kzg10::setup: h, beta_h, neg_powers_of_h]: out[i] = scalars[i] * h, written as
+ * ark-serialize `serialize_uncompressed` bytes (4 * sizeof(Fq) per point, infinity flag in the last byte).  h_uncompressed:
+ * the G2 base in the same byte form, or NULL for the curve's standard G2 generator.  Host-side (the prover never touches G2;
+ * a key needs 2 + #degree-bounds of these), no b2m_ctx needed. */
+int b2m_g2_scalar_muls(int curve, const uint8_t* h_uncompressed, const uint64_t* scalars, size_t n, uint8_t* out);
+
+/* G1 points between the device and ark-serialize files: powers_of_g[first .. first + n) of a resident SRS as
+ * `serialize_uncompressed` bytes (2 * sizeof(Fq) per point: canonical little-endian x || y, infinity flag = bit 6 of the last
+ * byte), and the inverse conversion of such bytes to the affine Montgomery limbs b2m_srs_create takes (no curve / subgroup
+ * check: like `deserialize_unchecked`).  Conversions run on the GPU. */
+int b2m_srs_export_g1(b2m_srs* srs, size_t first, size_t n, uint8_t* out);
+int b2m_g1_from_uncompressed(b2m_ctx* ctx, int curve, const uint8_t* bytes, size_t n, uint64_t* out_xy);
+int b2m_g1_to_uncompressed(b2m_ctx* ctx, int curve, const uint64_t* points_xy, size_t n, uint8_t* out);
+
 /* The caller's `zk_rng: &mut R` / `rng: Option<&mut dyn RngCore>` (reference src/lib.rs:154,125).  Two forms:
  *  - kind = B2M_RNG_CHACHA8/12/20, the fast path for the generators the reference's tests and benches use
  *    (`ark_std::test_rng()` = ChaCha12, `rand_chacha::ChaChaRng` = ChaCha20): the stream is described by its key and

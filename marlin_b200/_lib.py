@@ -74,6 +74,10 @@ def lib():
         L.b2m_srs_msm.argtypes = [vp, sz, vp, sz, vp, P(ci)]
         L.b2m_g1_powers.argtypes = [vp, ci, vp, vp, sz, vp]
         L.b2m_fixed_base_msm.argtypes = [vp, ci, vp, vp, sz, vp]
+        L.b2m_g2_scalar_muls.argtypes = [ci, vp, vp, sz, vp]
+        L.b2m_srs_export_g1.argtypes = [vp, sz, sz, vp]
+        L.b2m_g1_from_uncompressed.argtypes = [vp, ci, vp, sz, vp]
+        L.b2m_g1_to_uncompressed.argtypes = [vp, ci, vp, sz, vp]
         L.b2m_pc_commit.argtypes = [vp, ci, sz, vp, vp, vp, vp, P(Rng), vp, vp, vp, vp, sz]
         L.b2m_pc_open.argtypes = [vp, ci, sz, vp, vp, vp, vp, vp, sz, ctypes.c_int64, vp, vp, vp, P(ci), vp]
         L.b2m_trim.argtypes = [vp, ci, sz, sz, vp, sz, P(vp)]

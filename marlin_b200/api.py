@@ -111,6 +111,30 @@ class UniversalSRS:
     def __init__(self, ctx, curve_id, handle, max_degree, powers_limbs, gamma_limbs=None, gamma_indices=None):
         self.ctx, self.curve_id, self.handle, self.max_degree = ctx, curve_id, handle, max_degree
         self.powers_limbs, self.gamma_limbs, self.gamma_indices = powers_limbs, gamma_limbs, gamma_indices
+        self.trapdoor = None  # (beta, gamma) of an insecure test SRS made by universal_setup / srs_from_trapdoor
+        self.g2 = None        # (h, beta_h, {index: neg power}) as ark-serialize bytes when loaded from / written to a file
+
+    def save(self, path, degree_bounds=()):
+        """Write the SRS as an ark-serialize file (marlin_b200/srsfile.py).  The G2 half -- h, beta h and SonicKZG10's
+        beta^-(max_degree - d) h per enforced bound -- comes from the trapdoor of a test SRS, or from the file it was loaded from."""
+        from . import srsfile
+        L = _lib.lib()
+        g1 = 2 * srsfile.fq_bytes(self.curve_id)
+        n = self.max_degree + 1
+        powers = np.zeros(n * g1, dtype=np.uint8)
+        _lib.check(L.b2m_srs_export_g1(self.handle, 0, n, _lib.ptr(powers)))
+        gam = np.zeros(len(self.gamma_indices) * g1, dtype=np.uint8)
+        _lib.check(L.b2m_g1_to_uncompressed(self.ctx.handle, self.curve_id, _lib.ptr(np.ascontiguousarray(self.gamma_limbs)), len(self.gamma_indices),
+                                            _lib.ptr(gam)))
+        graw = gam.tobytes()
+        gamma = {int(k): graw[i * g1:(i + 1) * g1] for i, k in enumerate(self.gamma_indices)}
+        if self.trapdoor is not None:
+            h, beta_h, neg = srsfile.g2_setup(self.curve_id, fields.FR_MODULUS[self.curve_id], self.trapdoor[0], self.max_degree, degree_bounds)
+        elif self.g2 is not None:
+            h, beta_h, neg = self.g2
+        else:
+            raise ValueError("this SRS has no G2 half (neither a trapdoor nor a source file)")
+        srsfile.write_srs(path, self.curve_id, powers.tobytes(), gamma, h, beta_h, neg)
 
     def close(self):
         if self.handle:
@@ -193,7 +217,30 @@ class Marlin:
         exps = _lib.ints_to_limbs([pow(beta % r, i, r) for i in idx], 4)
         gam = np.zeros((len(idx), 2 * lq), dtype=np.uint64)
         _lib.check(L.b2m_fixed_base_msm(self.ctx.handle, cid, _lib.ptr(gamma_g), _lib.ptr(exps), len(idx), _lib.ptr(gam)))
-        return self.srs_from_points(powers, gam, idx, window_bits)
+        srs = self.srs_from_points(powers, gam, idx, window_bits)
+        srs.trapdoor = (beta % r, gamma % r)
+        return srs
+
+    def load_srs(self, path, window_bits=0):
+        """Load an SRS file (marlin_b200/srsfile.py layout; `deserialize_unchecked` semantics: no subgroup check)."""
+        from . import srsfile
+        L = _lib.lib()
+        d = srsfile.read_srs(path)
+        if d["curve_id"] != self.curve_id:
+            raise ValueError(f"{path} holds curve {d['curve_id']}, this Marlin instance is curve {self.curve_id}")
+        lq = _lib.LIMBS[self.curve_id][1]
+        g1 = 2 * srsfile.fq_bytes(self.curve_id)
+        n = len(d["powers"]) // g1
+        powers = np.zeros((n, 2 * lq), dtype=np.uint64)
+        raw = np.frombuffer(d["powers"], dtype=np.uint8)
+        _lib.check(L.b2m_g1_from_uncompressed(self.ctx.handle, self.curve_id, _lib.ptr(np.ascontiguousarray(raw)), n, _lib.ptr(powers)))
+        idx = sorted(d["gamma"])
+        graw = np.frombuffer(b"".join(d["gamma"][k] for k in idx), dtype=np.uint8)
+        gam = np.zeros((len(idx), 2 * lq), dtype=np.uint64)
+        _lib.check(L.b2m_g1_from_uncompressed(self.ctx.handle, self.curve_id, _lib.ptr(np.ascontiguousarray(graw)), len(idx), _lib.ptr(gam)))
+        srs = self.srs_from_points(powers, gam, idx, window_bits)
+        srs.g2 = (d["h"], d["beta_h"], d["neg_powers"])
+        return srs
 
     def srs_from_points(self, powers_limbs, gamma_limbs, gamma_indices, window_bits=0):
         """Upload an existing SRS (affine Montgomery limbs, as ark-ff stores them)."""

@@ -4,6 +4,7 @@
 #include "prover.cuh"
 #include "comm.cuh"
 #include <algorithm>
+#include "g2_host.hpp"
 
 namespace b2m {
 thread_local std::string g_last_error;
@@ -166,6 +167,93 @@ int b2m_fixed_base_msm(b2m_ctx* ctx, int curve, const uint64_t* g_xy, const uint
     ctx->cx.use();
     if (curve == B2M_CURVE_BLS12_381) Msm<FrBls, FqBls>::fixed_base_host(ctx->cx, g_xy, scalars, nullptr, 0, n, out_xy);
     else if (curve == B2M_CURVE_BN254) Msm<FrBn, FqBn>::fixed_base_host(ctx->cx, g_xy, scalars, nullptr, 0, n, out_xy);
+    else throw Error(B2M_ERR_INVALID_ARG, "unknown curve id");
+  });
+}
+
+int b2m_srs_export_g1(b2m_srs* srs, size_t first, size_t n, uint8_t* out) {
+  return guard([&] {
+    B2M_REQUIRE(srs && (out || n == 0), B2M_ERR_INVALID_ARG, "null argument");
+    B2M_REQUIRE(first + n <= srs->n_g, B2M_ERR_INVALID_ARG, "powers [%zu, %zu) of %zu", first, first + n, srs->n_g);
+    srs->ctx->cx.use();
+    if (srs->curve == B2M_CURVE_BLS12_381) {
+      B2M_REQUIRE(srs->bls->tab_world == 1, B2M_ERR_UNSUPPORTED, "export from a sharded key");
+      Msm<FrBls, FqBls>::g1_to_bytes(srs->ctx->cx, srs->bls->tables.p + first, nullptr, n, out);
+    } else {
+      B2M_REQUIRE(srs->bn->tab_world == 1, B2M_ERR_UNSUPPORTED, "export from a sharded key");
+      Msm<FrBn, FqBn>::g1_to_bytes(srs->ctx->cx, srs->bn->tables.p + first, nullptr, n, out);
+    }
+  });
+}
+int b2m_g1_to_uncompressed(b2m_ctx* ctx, int curve, const uint64_t* points_xy, size_t n, uint8_t* out) {
+  return guard([&] {
+    B2M_REQUIRE(ctx && ((points_xy && out) || n == 0), B2M_ERR_INVALID_ARG, "null argument");
+    ctx->cx.use();
+    if (curve == B2M_CURVE_BLS12_381) Msm<FrBls, FqBls>::g1_to_bytes(ctx->cx, nullptr, points_xy, n, out);
+    else if (curve == B2M_CURVE_BN254) Msm<FrBn, FqBn>::g1_to_bytes(ctx->cx, nullptr, points_xy, n, out);
+    else throw Error(B2M_ERR_INVALID_ARG, "unknown curve id");
+  });
+}
+int b2m_g1_from_uncompressed(b2m_ctx* ctx, int curve, const uint8_t* bytes, size_t n, uint64_t* out_xy) {
+  return guard([&] {
+    B2M_REQUIRE(ctx && ((bytes && out_xy) || n == 0), B2M_ERR_INVALID_ARG, "null argument");
+    ctx->cx.use();
+    if (curve == B2M_CURVE_BLS12_381) Msm<FrBls, FqBls>::g1_from_bytes(ctx->cx, bytes, n, out_xy);
+    else if (curve == B2M_CURVE_BN254) Msm<FrBn, FqBn>::g1_from_bytes(ctx->cx, bytes, n, out_xy);
+    else throw Error(B2M_ERR_INVALID_ARG, "unknown curve id");
+  });
+}
+
+}  // extern "C"
+// standard G2 generators (canonical x.c0, x.c1, y.c0, y.c1; big-endian hex), checked on-curve / order r in tests/test_srs_files.py
+static const char* const G2_GEN_BLS[4] = {
+    "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8",
+    "13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e",
+    "0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801",
+    "0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be"};
+static const char* const G2_GEN_BN[4] = {
+    "1800deef121f1e76426a00665e5c4479674322d4f75edadd46debd5cd992f6ed", "198e9393920d483a7260bfb731fb5d25f1aa493335a9e71297e485b7aef312c2",
+    "12c85ea5db8c6deb4aab71808dcb408fe3d1e7690c43d37b4ce6cc0166fa7daa", "090689d0585ff075ec9e99ad690c3395bc4b313370b38ef355acdadcd122975b"};
+
+template <class Fq>
+static Fq fq_from_hex(const char* hex) {
+  Fq c = Fq::zero();
+  const size_t len = strlen(hex);
+  for (size_t i = 0; i < len; i++) {
+    const char ch = hex[len - 1 - i];
+    const uint32_t v = ch >= 'a' ? ch - 'a' + 10 : ch - '0';
+    c.l[i / 8] |= v << (4 * (i % 8));
+  }
+  return Fq::from_canonical(c);
+}
+template <class Fq>
+static void g2_scalar_muls_impl(const char* const gen[4], const uint8_t* h_bytes, const uint64_t* scalars, size_t n, uint8_t* out) {
+  G2Jac<Fq> h;
+  if (h_bytes) {
+    Fq parts[4];
+    for (int k = 0; k < 4; k++) {
+      Fq c;
+      memcpy(c.l, h_bytes + (size_t)k * Fq::N * 4, Fq::N * 4);
+      if (k == 3) {
+        B2M_REQUIRE(!((c.l[Fq::N - 1] >> 30) & 1u), B2M_ERR_INVALID_ARG, "the G2 base is the point at infinity");
+        c.l[Fq::N - 1] &= 0x3fffffffu;
+      }
+      parts[k] = Fq::from_canonical(c);
+    }
+    h = G2Jac<Fq>{Fq2<Fq>{parts[0], parts[1]}, Fq2<Fq>{parts[2], parts[3]}, Fq2<Fq>::one()};
+  } else {
+    h = G2Jac<Fq>{Fq2<Fq>{fq_from_hex<Fq>(gen[0]), fq_from_hex<Fq>(gen[1])}, Fq2<Fq>{fq_from_hex<Fq>(gen[2]), fq_from_hex<Fq>(gen[3])}, Fq2<Fq>::one()};
+  }
+  std::vector<uint8_t> bytes;
+  for (size_t i = 0; i < n; i++) g2_write_uncompressed<Fq>(bytes, h.mul(reinterpret_cast<const uint32_t*>(scalars + 4 * i), 8));
+  memcpy(out, bytes.data(), bytes.size());
+}
+extern "C" {
+int b2m_g2_scalar_muls(int curve, const uint8_t* h_uncompressed, const uint64_t* scalars, size_t n, uint8_t* out) {
+  return guard([&] {
+    B2M_REQUIRE((scalars && out) || n == 0, B2M_ERR_INVALID_ARG, "null argument");
+    if (curve == B2M_CURVE_BLS12_381) g2_scalar_muls_impl<FqBls>(G2_GEN_BLS, h_uncompressed, scalars, n, out);
+    else if (curve == B2M_CURVE_BN254) g2_scalar_muls_impl<FqBn>(G2_GEN_BN, h_uncompressed, scalars, n, out);
     else throw Error(B2M_ERR_INVALID_ARG, "unknown curve id");
   });
 }

@@ -83,6 +83,9 @@ struct Msm {
   void run_host(size_t base_off, const uint64_t* scalars, size_t n, uint64_t* out_xy, int* out_is_inf);
   // powers_of_g[i] (affine Montgomery limbs) back to the host: window-0 table entry, from the GPU that holds it
   void read_power(size_t i, uint64_t* out_xy);
+  // affine Montgomery points <-> ark-serialize uncompressed bytes (canonical x || y, infinity flag in the last byte)
+  static void g1_to_bytes(Ctx& cx, const Affine<Fq>* dev_pts, const uint64_t* host_pts, size_t n, uint8_t* out);
+  static void g1_from_bytes(Ctx& cx, const uint8_t* bytes, size_t n, uint64_t* out_xy);
   static void g1_powers_host(Ctx& cx, const uint64_t* g_xy, const uint64_t* beta, size_t n, uint64_t* out);
   // out[i] = scalars[i] * g (canonical host scalars), or beta^(first + i) * g when scalars is null: windowed fixed-base
   // multiplication + batch normalisation [U ark-ec FixedBaseMSM::multi_scalar_mul as KZG10::setup uses it]

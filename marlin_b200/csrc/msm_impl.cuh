@@ -475,6 +475,27 @@ __global__ void __launch_bounds__(128) batch_normalize_kernel(const XYZZ<Fq>* pt
   }
 }
 
+// ---- ark-serialize uncompressed form of G1 points (SRS files) ----------------------------------------------------------------
+template <class Fq>
+__global__ void g1_canonical_kernel(const Affine<Fq>* in, size_t n, Affine<Fq>* out, bool to_bytes) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<Fq> p = ld_words(in + i);
+  if (to_bytes) {
+    const bool inf = p.is_inf();
+    p.x = p.x.to_canonical();
+    p.y = p.y.to_canonical();
+    if (inf) p.y.l[Fq::N - 1] |= 1u << 30;  // SWFlags::Infinity: bit 6 of the last byte
+  } else {
+    const bool inf = (p.y.l[Fq::N - 1] >> 30) & 1u;
+    p.y.l[Fq::N - 1] &= 0x3fffffffu;
+    p.x = Fq::from_canonical(p.x);
+    p.y = Fq::from_canonical(p.y);
+    if (inf) p = Affine<Fq>::inf();
+  }
+  st_words(out + i, p);
+}
+
 // ---- host driver ------------------------------------------------------------------------------
 template <class Fr, class Fq>
 int Msm<Fr, Fq>::pick_window(size_t n) {
@@ -898,6 +919,35 @@ void Msm<Fr, Fq>::fixed_base_host(Ctx& cx, const uint64_t* g_xy, const uint64_t*
     B2M_CHECK_LAUNCH();
     cx.launches += 2;
     aff.download(reinterpret_cast<Affine<Fq>*>(out) + at, m);
+  }
+}
+
+template <class Fr, class Fq>
+void Msm<Fr, Fq>::g1_to_bytes(Ctx& cx, const Affine<Fq>* dev_pts, const uint64_t* host_pts, size_t n, uint8_t* out) {
+  const size_t slice = (size_t)1 << 22;
+  DBuf<Affine<Fq>> in, conv(cx, std::min(n, slice) + 1);
+  if (!dev_pts) in = DBuf<Affine<Fq>>(cx, std::min(n, slice) + 1);
+  for (size_t at = 0; at < n; at += slice) {
+    const size_t m = std::min(slice, n - at);
+    const Affine<Fq>* src = dev_pts ? dev_pts + at : in.p;
+    if (!dev_pts) in.upload(reinterpret_cast<const Affine<Fq>*>(host_pts) + at, m);
+    g1_canonical_kernel<Fq><<<div_up(m, 256), 256, 0, cx.stream>>>(src, m, conv.p, true);
+    B2M_CHECK_LAUNCH();
+    cx.launches++;
+    conv.download(reinterpret_cast<Affine<Fq>*>(out) + at, m);
+  }
+}
+template <class Fr, class Fq>
+void Msm<Fr, Fq>::g1_from_bytes(Ctx& cx, const uint8_t* bytes, size_t n, uint64_t* out_xy) {
+  const size_t slice = (size_t)1 << 22;
+  DBuf<Affine<Fq>> in(cx, std::min(n, slice) + 1), conv(cx, std::min(n, slice) + 1);
+  for (size_t at = 0; at < n; at += slice) {
+    const size_t m = std::min(slice, n - at);
+    in.upload(reinterpret_cast<const Affine<Fq>*>(bytes) + at, m);
+    g1_canonical_kernel<Fq><<<div_up(m, 256), 256, 0, cx.stream>>>(in.p, m, conv.p, false);
+    B2M_CHECK_LAUNCH();
+    cx.launches++;
+    conv.download(reinterpret_cast<Affine<Fq>*>(out_xy) + at, m);
   }
 }
 

@@ -507,3 +507,45 @@ def test_destroy_order_is_free(b2m_ctx):
     assert len(proof) > 800
     ck.close()
     pk.close()
+
+
+def test_srs_file_save_load(gctx, tmp_path):
+    """an SRS generated on the GPU is written in ark-serialize layout (marlin_b200/srsfile.py), the G1 bytes are
+    the oracle's points in `serialize_uncompressed` form, and a key loaded back from the file proves the same bytes."""
+    import os
+    from marlin_b200 import srsfile
+    curve = BLS12_381
+    f = curve.fr
+    n = 16
+    m = api.Marlin("bls12_381", "sonic_kzg10", ctx=gctx)
+    beta = 0x1234567
+    srs = m.universal_setup(n, n, 3 * n, beta=beta, gamma=7, degree_bounds=(n - 2, 4 * n - 2))
+    path = os.path.join(tmp_path, "srs.bin")
+    circ = gr1cs.dummy_circuit(0, 3, 4, 10, n)
+    try:
+        srs.save(path, degree_bounds=(n - 2, 4 * n - 2))
+        d = srsfile.read_srs(path)
+        nb = curve.fq.nbytes
+        want = ec.fixed_base_powers(curve, curve.g, beta, srs.max_degree + 1)
+        for i in (0, 1, 2, srs.max_degree):
+            x = int.from_bytes(d["powers"][i * 2 * nb:i * 2 * nb + nb], "little")
+            y = int.from_bytes(d["powers"][i * 2 * nb + nb:(i + 1) * 2 * nb], "little")
+            assert (x, y) == want[i]
+        assert sorted(d["neg_powers"]) == sorted(srs.max_degree - b for b in (n - 2, 4 * n - 2))
+        pk = m.index(srs, circ)
+        proof = m.prove(pk, circ, api.ZkRng.test_rng())
+        vk = pk.vk_bytes
+        pk.close()
+    finally:
+        srs.close()
+    srs2 = m.load_srs(path)
+    try:
+        assert srs2.max_degree == 4 * n - 1
+        pk = m.index(srs2, circ)
+        try:
+            assert pk.vk_bytes == vk
+            assert m.prove(pk, circ, api.ZkRng.test_rng()) == proof
+        finally:
+            pk.close()
+    finally:
+        srs2.close()
