@@ -1,6 +1,6 @@
 //! Raw declarations, one for one with include/b2m.h.
 #![allow(non_camel_case_types)]
-use std::os::raw::{c_char, c_int, c_uint, c_ulonglong};
+use std::os::raw::{c_char, c_int, c_uint, c_ulonglong, c_void};
 
 #[repr(C)]
 pub struct b2m_ctx {
@@ -15,18 +15,27 @@ pub struct b2m_index {
     _p: [u8; 0],
 }
 #[repr(C)]
+pub struct b2m_ck {
+    _p: [u8; 0],
+}
+#[repr(C)]
 pub struct b2m_matrix {
     pub row_ptr: *const u64,
     pub col: *const u64,
     pub coeff: *const u64,
 }
+/// `b2m_rng` (include/b2m.h): a ChaCha stream position (kind = 8 / 12 / 20) or, with kind = B2M_RNG_CALLBACK, any `RngCore`
+/// reached through `next_u64(state)`.
 #[repr(C)]
 #[derive(Clone, Copy)]
 pub struct b2m_rng {
     pub kind: c_int,
     pub key: [u8; 32],
     pub word_pos: u64,
+    pub next_u64: Option<unsafe extern "C" fn(state: *mut c_void) -> u64>,
+    pub state: *mut c_void,
 }
+pub const B2M_RNG_CALLBACK: c_int = 1;
 
 pub const B2M_OK: c_int = 0;
 pub const B2M_ERR_INVALID_ARG: c_int = 1;
@@ -67,6 +76,22 @@ extern "C" {
                        degree_bounds: *const i64, rands: *const u64, shifted_rands: *const u64, rand_stride: usize,
                        max_degree_bound: i64, point: *const u64, opening_challenge: *const u64, out_w_xy: *mut u64,
                        out_has_random_v: *mut c_int, out_random_v: *mut u64) -> c_int;
+    pub fn b2m_g1_powers(ctx: *mut b2m_ctx, curve: c_int, g_xy: *const u64, beta: *const u64, n: usize, out_powers_xy: *mut u64) -> c_int;
+    pub fn b2m_fixed_base_msm(ctx: *mut b2m_ctx, curve: c_int, g_xy: *const u64, scalars: *const u64, n: usize, out_xy: *mut u64) -> c_int;
+    pub fn b2m_trim(srs: *mut b2m_srs, pc_variant: c_int, supported_degree: usize, supported_hiding_bound: usize,
+                    enforced_degree_bounds: *const u64, n_bounds: usize, out: *mut *mut b2m_ck) -> c_int;
+    pub fn b2m_ck_destroy(ck: *mut b2m_ck);
+    pub fn b2m_ck_supported_degree(ck: *const b2m_ck) -> usize;
+    pub fn b2m_ck_shift_power(ck: *const b2m_ck, bound: u64, out_xy: *mut u64) -> c_int;
+    pub fn b2m_ck_commit(ck: *mut b2m_ck, n_polys: usize, coeffs: *const *const u64, n_coeffs: *const usize, degree_bounds: *const i64,
+                         hiding_bounds: *const i64, rng: *mut b2m_rng, out_comm_xy: *mut u64, out_shifted_xy: *mut u64, out_rand: *mut u64,
+                         out_shifted_rand: *mut u64, rand_stride: usize) -> c_int;
+    pub fn b2m_ck_open_combinations(ck: *mut b2m_ck, n_polys: usize, coeffs: *const *const u64, n_coeffs: *const usize,
+                                    degree_bounds: *const i64, hiding: *const c_int, rands: *const u64, shifted_rands: *const u64,
+                                    rand_stride: usize, n_lcs: usize, lc_term_off: *const usize, lc_poly: *const i64, lc_coeff: *const u64,
+                                    n_queries: usize, query_lc: *const usize, query_point: *const usize, n_points: usize,
+                                    points: *const u64, opening_challenge: *const u64, out_w_xy: *mut u64, out_has_random_v: *mut c_int,
+                                    out_random_v: *mut u64) -> c_int;
     pub fn b2m_index_create(srs: *mut b2m_srs, pc_variant: c_int, num_constraints: usize, num_variables: usize,
                             num_instance_variables: usize, a: *const b2m_matrix, b: *const b2m_matrix, c: *const b2m_matrix,
                             out: *mut *mut b2m_index) -> c_int;

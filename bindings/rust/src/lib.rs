@@ -9,9 +9,14 @@
 //!                     (`src/lib.rs:151-311`); the proof comes back as ark-serialize bytes and is deserialised into the
 //!                     reference's own `Proof` type, so `Marlin::verify` (`src/lib.rs:315-433`) runs unchanged on the CPU.
 //!
+//!  * `pc::B200MarlinKZG10` / `pc::B200SonicKZG10` implement `PolynomialCommitment` (the generic parameter `PC` of
+//!                     `Marlin<F, PC, FS>`, `src/lib.rs:64-71`): `setup` / `check*` delegate to ark-poly-commit, `trim` / `commit` /
+//!                     `open*` run on the GPU, so `Marlin::<Fr, B200MarlinKZG10, FS>::{index, prove, verify}` is the stock code.
+//!
 //! This crate has NOT been compiled (the build image has no Rust toolchain); the C side it binds is tested through the
 //! Python ctypes twin of these declarations (marlin_b200/_lib.py, tests/).
 pub mod ffi;
+pub mod pc;
 
 use ark_bls12_381::{Bls12_381, Fq, Fr, G1Affine, G1Projective};
 use ark_ec::{AffineCurve, ProjectiveCurve};
@@ -42,7 +47,7 @@ pub enum Error {
     Device(c_int, String),
 }
 
-fn check(code: c_int) -> Result<(), Error> {
+pub(crate) fn check(code: c_int) -> Result<(), Error> {
     use ffi::*;
     match code {
         B2M_OK => Ok(()),
@@ -68,7 +73,7 @@ fn fq_from_limbs(l: &[u64]) -> Fq {
     a.copy_from_slice(&l[..6]);
     Fq::new(BigInteger384(a)) // `new` takes the Montgomery representation as is
 }
-fn g1_limbs(p: &G1Affine, out: &mut Vec<u64>) {
+pub(crate) fn g1_limbs(p: &G1Affine, out: &mut Vec<u64>) {
     if p.infinity {
         out.extend_from_slice(&[0u64; 12]);
     } else {
@@ -76,7 +81,7 @@ fn g1_limbs(p: &G1Affine, out: &mut Vec<u64>) {
         out.extend_from_slice(&fq_limbs(&p.y));
     }
 }
-fn g1_from_limbs(l: &[u64], is_inf: bool) -> G1Affine {
+pub(crate) fn g1_from_limbs(l: &[u64], is_inf: bool) -> G1Affine {
     if is_inf || l[..12].iter().all(|w| *w == 0) {
         G1Affine::zero()
     } else {
@@ -94,7 +99,7 @@ pub fn fr_canonical_limbs(v: &[Fr]) -> Vec<u64> {
 
 /// One GPU (one CUDA device + streams).  Not `Sync`: use one context per thread.
 pub struct Context {
-    raw: *mut ffi::b2m_ctx,
+    pub(crate) raw: *mut ffi::b2m_ctx,
 }
 impl Context {
     pub fn new(device: i32) -> Result<Self, Error> {
@@ -180,13 +185,17 @@ fn to_csr(m: &[Vec<(Fr, usize)>]) -> Csr {
     Csr { row_ptr, col, coeff }
 }
 
-/// The padding the reference applies before indexing and proving (`src/ahp/constraint_systems.rs:45-81`): public inputs
-/// up to a power of two with zeros, then dummy constraints or dummy witnesses (value one) until the matrices are square.
-fn pad_like_the_reference(cs: &ark_relations::r1cs::ConstraintSystemRef<Fr>) -> Result<(), Error> {
+/// `pad_input_for_indexer_and_prover` (`src/ahp/constraint_systems.rs:45-58`): public inputs up to a power of two with zeros.
+fn pad_input_for_indexer_and_prover(cs: &ark_relations::r1cs::ConstraintSystemRef<Fr>) -> Result<(), Error> {
     let n_in = cs.num_instance_variables();
     for _ in n_in..n_in.next_power_of_two() {
         cs.new_input_variable(|| Ok(Fr::zero())).map_err(Error::Synthesis)?;
     }
+    Ok(())
+}
+/// `make_matrices_square_for_indexer` / `_for_prover` (`src/ahp/constraint_systems.rs:60-81`), applied AFTER `finalize()`:
+/// dummy constraints or dummy witnesses (value one) until #constraints == #variables.
+fn make_matrices_square(cs: &ark_relations::r1cs::ConstraintSystemRef<Fr>) -> Result<(), Error> {
     let vars = cs.num_instance_variables() + cs.num_witness_variables();
     let cons = cs.num_constraints();
     if vars > cons {
@@ -215,8 +224,11 @@ impl<'s> IndexProverKey<'s> {
         cs.set_optimization_goal(OptimizationGoal::Weight);
         cs.set_mode(SynthesisMode::Setup);
         circuit.generate_constraints(cs.clone()).map_err(Error::Synthesis)?;
-        pad_like_the_reference(&cs)?;
+        // the reference's order (src/ahp/indexer.rs:160-166): pad the public input, finalize (which may OUTLINE linear
+        // combinations into new witnesses and constraints), and only then square the matrices
+        pad_input_for_indexer_and_prover(&cs)?;
         cs.finalize();
+        make_matrices_square(&cs)?;
         let m: ConstraintMatrices<Fr> = cs.to_matrices().expect("matrices in setup mode");
         let (a, b, c) = (to_csr(&m.a), to_csr(&m.b), to_csr(&m.c));
         let view = |x: &Csr| ffi::b2m_matrix { row_ptr: x.row_ptr.as_ptr(), col: x.col.as_ptr(), coeff: x.coeff.as_ptr() };
@@ -241,23 +253,49 @@ impl<'s> IndexProverKey<'s> {
         C: ConstraintSynthesizer<Fr>,
         PC: ark_poly_commit::PolynomialCommitment<Fr, ark_poly::univariate::DensePolynomial<Fr>>,
     {
+        // fast path: `ark_std::test_rng()` / StdRng streams are described by (key, word position) and sampled on the device
+        let mut rng = ffi::b2m_rng { kind: 12, key: zk_rng.get_seed(), word_pos: zk_rng.get_word_pos() as u64, next_u64: None,
+                                     state: std::ptr::null_mut() };
+        let proof = self.prove_with(circuit, &mut rng)?;
+        zk_rng.set_word_pos(rng.word_pos as u128);
+        Ok(proof)
+    }
+
+    /// `Marlin::prove` with ANY `RngCore` as `zk_rng` (reference src/lib.rs:154): every draw goes through the callback form of
+    /// `b2m_rng`, in the reference's order.
+    pub fn prove_with_rng<C, PC, R: rand_core::RngCore>(&self, circuit: C, zk_rng: &mut R) -> Result<ark_marlin::Proof<Fr, PC>, Error>
+    where
+        C: ConstraintSynthesizer<Fr>,
+        PC: ark_poly_commit::PolynomialCommitment<Fr, ark_poly::univariate::DensePolynomial<Fr>>,
+    {
+        let mut dynrng: &mut dyn rand_core::RngCore = zk_rng;
+        let mut rng = pc::callback_rng(&mut dynrng);
+        self.prove_with(circuit, &mut rng)
+    }
+
+    fn prove_with<C, PC>(&self, circuit: C, rng: &mut ffi::b2m_rng) -> Result<ark_marlin::Proof<Fr, PC>, Error>
+    where
+        C: ConstraintSynthesizer<Fr>,
+        PC: ark_poly_commit::PolynomialCommitment<Fr, ark_poly::univariate::DensePolynomial<Fr>>,
+    {
         let cs = ConstraintSystem::<Fr>::new_ref();
         cs.set_optimization_goal(OptimizationGoal::Weight);
-        cs.set_mode(SynthesisMode::Prove { construct_matrices: false });
+        // construct_matrices: true like the reference (src/ahp/prover.rs:220-222): finalize() outlines linear combinations
+        // only when it builds the matrices, and the outlining adds witnesses that must exist in the assignment
+        cs.set_mode(SynthesisMode::Prove { construct_matrices: true });
         circuit.generate_constraints(cs.clone()).map_err(Error::Synthesis)?;
-        pad_like_the_reference(&cs)?;
+        pad_input_for_indexer_and_prover(&cs)?;  // src/ahp/prover.rs:227-229: same order as the indexer
         cs.finalize();
+        make_matrices_square(&cs)?;
         let inner = cs.borrow().expect("constraint system");
         let x = fr_mont_limbs(&inner.instance_assignment);
         let w = fr_mont_limbs(&inner.witness_assignment);
-        let mut rng = ffi::b2m_rng { kind: 12, key: zk_rng.get_seed(), word_pos: zk_rng.get_word_pos() as u64 };
         let mut buf = vec![0u8; 4096];
         let mut len = 0usize;
         check(unsafe {
-            ffi::b2m_prove(self.raw, x.as_ptr(), inner.instance_assignment.len(), w.as_ptr(), inner.witness_assignment.len(), &mut rng,
+            ffi::b2m_prove(self.raw, x.as_ptr(), inner.instance_assignment.len(), w.as_ptr(), inner.witness_assignment.len(), rng,
                            buf.as_mut_ptr(), buf.len(), &mut len)
         })?;
-        zk_rng.set_word_pos(rng.word_pos as u128);
         ark_marlin::Proof::<Fr, PC>::deserialize(&buf[..len]).map_err(Error::Serialization)
     }
 }

@@ -514,8 +514,8 @@ def test_srs_file_save_load(gctx, tmp_path):
     the oracle's points in `serialize_uncompressed` form, and a key loaded back from the file proves the same bytes."""
     import os
     from marlin_b200 import srsfile
+    from oracle import ec
     curve = BLS12_381
-    f = curve.fr
     n = 16
     m = api.Marlin("bls12_381", "sonic_kzg10", ctx=gctx)
     beta = 0x1234567
