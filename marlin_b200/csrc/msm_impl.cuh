@@ -220,11 +220,13 @@ struct MsmLongRun {
   uint32_t dst;                  // MSM_NO_DIGIT: the run's sum is the bucket; else: chunk-partial slot it goes to
 };
 constexpr uint32_t MSM_RUN_CHUNK = 256;  // slots one warp folds; longer runs are cut into chunks + one second-stage entry
+constexpr uint32_t MSM_RUN_SHORT = 32;   // runs of up to this many slots are folded by ONE thread each (many short runs: the
+                                         // full top window of an XYZZ-only pass gives every one of its 2^14 buckets a 6-12 slot run)
 template <class Fq>
 __global__ void __launch_bounds__(128)
 msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nthreads, const uint32_t q, const uint32_t* offsets,
-                  const uint32_t* ends, XYZZ<Fq>* buckets, MsmLongRun* long_runs, MsmLongRun* final_runs, uint32_t* n_long, uint32_t long_cap,
-                  uint32_t chunk_cap) {
+                  const uint32_t* ends, XYZZ<Fq>* buckets, MsmLongRun* long_runs, MsmLongRun* final_runs, MsmLongRun* short_runs, uint32_t* n_long,
+                  uint32_t long_cap, uint32_t chunk_cap) {
   // One thread per accumulate-thread u.  A run of partials starts either in u's tail slot (a bucket that
   // begins inside u's range and continues into u + 1) or in u's head slot when the bucket begins exactly at
   // u's first reference; u can hold only one of the two.  The common run is the pair (tail of u, head of
@@ -241,9 +243,15 @@ msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nthr
   const uint32_t t1 = (ends[b] - 1u) / q;  // thread holding the bucket's last reference
   const uint32_t last = 2u * t1;                          // its head slot closes the run
   if (t1 > (uint32_t)u + 1u) {
-    // n_long[0]: queued (first-stage) entries, [1]: second-stage entries, [2]: chunk-partial slots handed out
+    // n_long[0]: queued (first-stage) entries, [1]: second-stage entries, [2]: chunk-partial slots handed out, [3]: short runs
     const uint32_t nslots = last - first + 1u;
-    if (nslots <= MSM_RUN_CHUNK) {
+    if (nslots <= MSM_RUN_SHORT) {
+      const uint32_t slot = atomicAdd(n_long + 3, 1u);
+      if (slot < long_cap) {
+        short_runs[slot] = MsmLongRun{first, last, b, MSM_NO_DIGIT};
+        return;
+      }
+    } else if (nslots <= MSM_RUN_CHUNK) {
       const uint32_t slot = atomicAdd(n_long, 1u);
       if (slot < long_cap) {
         long_runs[slot] = MsmLongRun{first, last, b, MSM_NO_DIGIT};
@@ -280,6 +288,21 @@ msm_stitch_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, size_t nthr
 // shared memory; runs of more than MSM_RUN_CHUNK slots were queued as chunks whose sums a second launch (FINAL) adds up.
 // (Round 1 folded runs of up to 256 slots serially in one thread -- 256 dependent XYZZ additions, ~2 ms of latency per
 // MSM -- and longer ones in one block each: `msm_stitch` grew from 1.3 ms to 8-13 ms per proof on 4 and 8 GPUs.)
+// short runs: one thread per run, all lanes busy
+template <class Fq>
+__global__ void __launch_bounds__(128)
+msm_stitch_short_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, const MsmLongRun* runs, const uint32_t* n_runs, uint32_t cap,
+                        XYZZ<Fq>* buckets) {
+  uint32_t count = *n_runs;
+  if (count > cap) count = cap;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x) {
+    const MsmLongRun run = runs[r];
+    XYZZ<Fq> acc = ld_words(part_pt + run.first);
+    for (uint32_t k = run.first + 1; k <= run.last; k++)
+      if (part_bkt[k] == run.bucket) g1_add(acc, ld_words(part_pt + k));
+    st_words(buckets + run.bucket, acc);
+  }
+}
 template <class Fq, bool FINAL>
 __global__ void __launch_bounds__(128)
 msm_stitch_runs_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, const MsmLongRun* runs, const uint32_t* n_runs, uint32_t cap,
@@ -658,10 +681,10 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       digits[s] = DBuf<uint32_t>(cx, max_refs); hist[s] = DBuf<uint32_t>(cx, B + 1); offsets[s] = DBuf<uint32_t>(cx, B + 1);
       cursor[s] = DBuf<uint32_t>(cx, B); sorted[s] = DBuf<uint2>(cx, max_refs);
     }
-    DBuf<uint32_t> part_bkt(cx, 2 * max_threads), n_long(cx, 3);  // queued long-run entries, second-stage entries, chunk slots
+    DBuf<uint32_t> part_bkt(cx, 2 * max_threads), n_long(cx, 4);  // queued long-run entries, second-stage entries, chunk slots, short runs
     const uint32_t long_cap = 1u << 18;
     const uint32_t chunk_cap = (uint32_t)(4 * max_threads / MSM_RUN_CHUNK + 4);  // every chunk but a run's last covers MSM_RUN_CHUNK slots
-    DBuf<MsmLongRun> long_runs(cx, long_cap), final_runs(cx, chunk_cap);
+    DBuf<MsmLongRun> long_runs(cx, long_cap), short_runs(cx, long_cap), final_runs(cx, chunk_cap);
     DBuf<XYZZ<Fq>> chunk_pt(cx, chunk_cap);
     DBuf<XYZZ<Fq>> part_pt(cx, 2 * max_threads);
     // batched-affine levels (msm_affine.cuh): level l has at most bound[l] points
@@ -803,14 +826,16 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       size_t sp1 = cx.span_begin("msm_stitch", (double)n);
       n_long.zero();
       msm_stitch_kernel<Fq><<<div_up(nthreads, 128), 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, nthreads, q, src_off, src_ends,
-                                                                           buckets.p + (size_t)j * B, long_runs.p, final_runs.p, n_long.p, long_cap,
-                                                                           chunk_cap);
+                                                                           buckets.p + (size_t)j * B, long_runs.p, final_runs.p, short_runs.p, n_long.p,
+                                                                           long_cap, chunk_cap);
+      msm_stitch_short_kernel<Fq><<<2 * cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, short_runs.p, n_long.p + 3, long_cap,
+                                                                          buckets.p + (size_t)j * B);
       msm_stitch_runs_kernel<Fq, false><<<4 * cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, long_runs.p, n_long.p, long_cap,
                                                                                 buckets.p + (size_t)j * B, chunk_pt.p);
       msm_stitch_runs_kernel<Fq, true><<<cx.sm_count, 128, 0, cx.stream>>>(part_pt.p, part_bkt.p, final_runs.p, n_long.p + 1, chunk_cap,
                                                                            buckets.p + (size_t)j * B, chunk_pt.p);
       B2M_CHECK_LAUNCH();
-      cx.launches += 3;
+      cx.launches += 4;
       cx.span_end(sp1);
       B2M_CUDA(cudaEventRecord(ev_acc[j], cx.stream));
     }
