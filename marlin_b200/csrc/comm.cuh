@@ -14,6 +14,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 
@@ -26,9 +27,10 @@ struct NcclApi {
       api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.handle, "ncclGetUniqueId"));
       api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.handle, "ncclCommInitRank"));
       api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.handle, "ncclAllGather"));
+      api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(api.handle, "ncclBroadcast"));
       api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
       api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
-      B2M_REQUIRE(api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy, B2M_ERR_NCCL, "libnccl lacks a required symbol");
+      B2M_REQUIRE(api.GetUniqueId && api.CommInitRank && api.AllGather && api.Broadcast && api.CommDestroy, B2M_ERR_NCCL, "libnccl lacks a required symbol");
     }
     return api;
   }
@@ -46,6 +48,11 @@ struct NcclApi {
 
 inline void all_gather_bytes(Ctx& cx, const void* send, void* recv, size_t bytes_per_rank) {
   B2M_NCCL(NcclApi::get().AllGather(send, recv, bytes_per_rank, ncclUint8, static_cast<ncclComm_t>(cx.comm), cx.stream));
+}
+
+// in-place broadcast of `bytes` from rank `root` (every rank passes the same buffer size)
+inline void broadcast_bytes(Ctx& cx, void* buf, size_t bytes, int root) {
+  B2M_NCCL(NcclApi::get().Broadcast(buf, buf, bytes, ncclUint8, root, static_cast<ncclComm_t>(cx.comm), cx.stream));
 }
 
 }  // namespace b2m

@@ -220,7 +220,7 @@ struct MsmLongRun {
   uint32_t dst;                  // MSM_NO_DIGIT: the run's sum is the bucket; else: chunk-partial slot it goes to
 };
 constexpr uint32_t MSM_RUN_CHUNK = 256;  // slots one warp folds; longer runs are cut into chunks + one second-stage entry
-constexpr uint32_t MSM_RUN_SHORT = 32;   // runs of up to this many slots are folded by ONE thread each (many short runs: the
+constexpr uint32_t MSM_RUN_SHORT = 12;   // runs of up to this many slots are folded by ONE thread each (many short runs: the
                                          // full top window of an XYZZ-only pass gives every one of its 2^14 buckets a 6-12 slot run)
 template <class Fq>
 __global__ void __launch_bounds__(128)

@@ -20,6 +20,7 @@
 #include "hostutil.hpp"
 #include "poly_impl.cuh"
 #include "prover.cuh"
+#include "comm.cuh"
 #include "scan.cuh"
 
 namespace b2m {
@@ -353,6 +354,33 @@ struct MarlinIndex : IndexBase {
     if (n > len) B2M_CUDA(cudaMemsetAsync(work.p + len, 0, (n - len) * sizeof(Fr), cx.stream));
     ntt.run(work.p, out, log_n, false);
   }
+  // A group of INDEPENDENT transforms of one round.  One GPU: run them in order.  Several GPUs (the prover is replicated, so
+  // every rank holds every input): transform j is computed by rank j mod world only and its result broadcast over NVLink --
+  // north_star keeps a single NTT on one GPU, but a round's independent transforms need not all run on the same one.  Worth it
+  // from ~2^22 points on (a broadcast of 134 MB costs about a third of the transform); at 2^24 constraints on 8 GPUs the NTTs
+  // are the largest term of the proof.  Results are bit-identical either way.
+  struct NttJob {
+    const Fr* coeffs;  // padded form: `len` coefficients zero-extended to 2^log_n (work == nullptr)
+    size_t len;
+    Fr* work;          // direct form: 2^log_n values, overwritten
+    Fr* out;
+    int log_n;
+    bool inverse;
+  };
+  int ntt_share_min_log = 22;
+  void run_ntt_group(const std::vector<NttJob>& jobs) {
+    const bool share = cx.world > 1 && cx.comm != nullptr && jobs.size() > 1 && jobs[0].log_n >= ntt_share_min_log;
+    for (size_t j = 0; j < jobs.size(); j++) {
+      if (share && (int)(j % (size_t)cx.world) != cx.rank) continue;
+      const NttJob& q = jobs[j];
+      if (q.work) ntt.run(q.work, q.out, q.log_n, q.inverse);
+      else fft_padded(q.coeffs, q.len, q.log_n, q.out);
+    }
+    if (!share) return;
+    size_t sp = cx.span_begin("ntt_broadcast", 0.0);
+    for (size_t j = 0; j < jobs.size(); j++) broadcast_bytes(cx, jobs[j].out, sizeof(Fr) << jobs[j].log_n, (int)(j % (size_t)cx.world));
+    cx.span_end(sp);
+  }
   Fr download_fr(const Fr* p) {
     Fr h;
     B2M_CUDA(cudaMemcpyAsync(&h, p, sizeof(Fr), cudaMemcpyDeviceToHost, cx.stream));
@@ -477,6 +505,7 @@ struct MarlinIndex : IndexBase {
     B2M_REQUIRE(rng->kind == B2M_RNG_CHACHA8 || rng->kind == B2M_RNG_CHACHA12 || rng->kind == B2M_RNG_CHACHA20 ||
                     (rng->kind == B2M_RNG_CALLBACK && rng->next_u64 != nullptr),
                 B2M_ERR_MISSING_RNG, "unsupported rng kind %d", rng->kind);
+    if (const char* e = getenv("B2M_NTT_SHARE_MIN_LOG")) ntt_share_min_log = atoi(e);
     Timer tm(cx);
     size_t t_all = tm.begin("Marlin::Prover");
     ZkSource<b2m_rng> zk(rng);
@@ -518,6 +547,7 @@ struct MarlinIndex : IndexBase {
       ntt.run(xw.p, x_poly.p, log_x, true);
     }
     DBuf<Fr> wt(cx, H + 1);  // (iFFT_H(w - x) + rho v_H); w_poly = its suffix sums shifted by |X|
+    DBuf<Fr> za_poly(cx, H + 1), zb_poly(cx, H + 1);
     {
       DBuf<Fr> x_evals(cx, H), w_evals(cx, H);
       fft_padded(x_poly.p, X, log_h, x_evals.p);
@@ -532,15 +562,15 @@ struct MarlinIndex : IndexBase {
         }
         st_fr(pwe + k, v);
       });
-      ntt.run(w_evals.p, wt.p, log_h, true);
+      run_ntt_group({NttJob{nullptr, 0, w_evals.p, wt.p, log_h, true}, NttJob{nullptr, 0, z_a.p, za_poly.p, log_h, true},
+                     NttJob{nullptr, 0, z_b.p, zb_poly.p, log_h, true}});
     }
     Fr rho_w = field_rand<Fr>(zk), rho_a = field_rand<Fr>(zk), rho_b = field_rand<Fr>(zk);
     blind(wt.p, rho_w);
     rec_suffix<Fr>(cx, wt.p, wt.p, H + 1, X, one, false);  // divide by v_X: q[i] = S[i + |X|]
     Oracle o_w; o_w.p = wt.p + X; o_w.len = H + 1 - X; o_w.hiding = true;
-    DBuf<Fr> za_poly(cx, H + 1), zb_poly(cx, H + 1);
-    ntt.run(z_a.p, za_poly.p, log_h, true); blind(za_poly.p, rho_a);
-    ntt.run(z_b.p, zb_poly.p, log_h, true); blind(zb_poly.p, rho_b);
+    blind(za_poly.p, rho_a);
+    blind(zb_poly.p, rho_b);
     Oracle o_za; o_za.p = za_poly.p; o_za.len = H + 1; o_za.hiding = true;
     Oracle o_zb; o_zb.p = zb_poly.p; o_zb.len = H + 1; o_zb.hiding = true;
     // mask polynomial: 3|H| rejection-sampled coefficients straight from the ChaCha stream
@@ -568,8 +598,7 @@ struct MarlinIndex : IndexBase {
     DBuf<Fr> summed_ev(cx, M);  // evaluations of eta_c z_a z_b + eta_a z_a + eta_b z_b on 4|H|
     {
       DBuf<Fr> ea(cx, M), eb(cx, M);
-      fft_padded(za_poly.p, H + 1, log_m, ea.p);
-      fft_padded(zb_poly.p, H + 1, log_m, eb.p);
+      run_ntt_group({NttJob{za_poly.p, H + 1, nullptr, ea.p, log_m, false}, NttJob{zb_poly.p, H + 1, nullptr, eb.p, log_m, false}});
       const Fr* pa = ea.p; const Fr* pb = eb.p; Fr* ps = summed_ev.p;
       ew(cx, M, [=] __device__(size_t i) {
         Fr x = ld_fr(pa + i), y = ld_fr(pb + i);
@@ -584,9 +613,6 @@ struct MarlinIndex : IndexBase {
       ew(cx, H, [=] __device__(size_t i) { st_fr(pr + i, alpha - domain_element(tw, ml, lh, i)); });
       batch_inverse<Fr>(cx, r_alpha_ev.p, H);
       ew(cx, H, [=] __device__(size_t i) { st_fr(pr + i, ld_fr(pr + i) * v_h_alpha); });
-      DBuf<Fr> work(cx, H);
-      B2M_CUDA(cudaMemcpyAsync(work.p, r_alpha_ev.p, H * sizeof(Fr), cudaMemcpyDeviceToDevice, cx.stream));
-      ntt.run(work.p, r_alpha_poly.p, log_h, true);
     }
     // t(X): segmented sums of eta_M * M[r][c] * r(alpha, w^r) by reindexed column  [reference prover.rs:411-428]
     {
@@ -603,7 +629,8 @@ struct MarlinIndex : IndexBase {
       rec_suffix<Fr>(cx, prod.p, prod.p, ne + 1, 1, one, false);  // suffix sums
       const uint32_t* pcp = t_colptr.p; Fr* pt = t_ev.p;
       ew(cx, H, [=] __device__(size_t j) { st_fr(pt + j, ld_fr(pp + pcp[j]) - ld_fr(pp + pcp[j + 1])); });
-      ntt.run(t_ev.p, t_poly.p, log_h, true);
+      // r(alpha, X) and t(X) by interpolation on H: two independent transforms (r_alpha_ev is not read again)
+      run_ntt_group({NttJob{nullptr, 0, r_alpha_ev.p, r_alpha_poly.p, log_h, true}, NttJob{nullptr, 0, t_ev.p, t_poly.p, log_h, true}});
     }
     // z(X) = w(X) v_X(X) + x(X)    [reference prover.rs:501-518]
     DBuf<Fr> z_poly(cx, H + 1);
@@ -621,9 +648,8 @@ struct MarlinIndex : IndexBase {
     DBuf<Fr> g1(cx, H), h1(cx, 2 * H);
     {
       DBuf<Fr> er(cx, M), ez(cx, M), et(cx, M), rhs(cx, M);
-      fft_padded(r_alpha_poly.p, H, log_m, er.p);
-      fft_padded(z_poly.p, H + 1, log_m, ez.p);
-      fft_padded(t_poly.p, H, log_m, et.p);
+      run_ntt_group({NttJob{r_alpha_poly.p, H, nullptr, er.p, log_m, false}, NttJob{z_poly.p, H + 1, nullptr, ez.p, log_m, false},
+                     NttJob{t_poly.p, H, nullptr, et.p, log_m, false}});
       Fr* pr = er.p; const Fr* ps = summed_ev.p; const Fr* pz = ez.p; const Fr* pt = et.p;
       ew(cx, M, [=] __device__(size_t i) { st_fr(pr + i, ld_fr(pr + i) * ld_fr(ps + i) - ld_fr(pz + i) * ld_fr(pt + i)); });
       ntt.run(er.p, rhs.p, log_m, true);
@@ -671,12 +697,10 @@ struct MarlinIndex : IndexBase {
       ew(cx, K, [=] __device__(size_t i) {
         st_fr(pf + i, ld_fr(pf + i) * (ea_v * ld_fr(pva + i) + eb_v * ld_fr(pvb + i) + ec_v * ld_fr(pvc + i)));
       });
-      ntt.run(b_ev.p, b_poly.p, log_k, true);
-      ntt.run(f_ev.p, f_poly.p, log_k, true);
+      run_ntt_group({NttJob{nullptr, 0, b_ev.p, b_poly.p, log_k, true}, NttJob{nullptr, 0, f_ev.p, f_poly.p, log_k, true}});
       // b * f on 2|K|; h_2 = (a - b f) / v_K = -(b f)[|K| ..]
       DBuf<Fr> eb2(cx, 2 * K), ef2(cx, 2 * K), bf(cx, 2 * K);
-      fft_padded(b_poly.p, K, log_k + 1, eb2.p);
-      fft_padded(f_poly.p, K, log_k + 1, ef2.p);
+      run_ntt_group({NttJob{b_poly.p, K, nullptr, eb2.p, log_k + 1, false}, NttJob{f_poly.p, K, nullptr, ef2.p, log_k + 1, false}});
       Fr* p1 = eb2.p; const Fr* p2 = ef2.p;
       ew(cx, 2 * K, [=] __device__(size_t i) { st_fr(p1 + i, ld_fr(p1 + i) * ld_fr(p2 + i)); });
       ntt.run(eb2.p, bf.p, log_k + 1, true);
