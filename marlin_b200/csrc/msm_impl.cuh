@@ -344,31 +344,82 @@ msm_stitch_runs_kernel(const XYZZ<Fq>* part_pt, const uint32_t* part_bkt, const 
 //     Rsum[hi] = sum_lo B[hi][lo]  (row tree),   Csum[lo] = sum_hi B[hi][lo]  (column tree),
 // and each of the two short weighted sums is done by bit planes: sum_i i V_i = sum_k 2^k sum_{i: bit k} V_i.
 
-// Segmented sums, the building block of both trees:
-//     out[(g * nseg + s) * ni + i] = sum_{k < K} in[g * group_stride + (s * K + k) * stride_k + i * stride_i]
-// One thread per output, K serial additions each (fully inlined: a call per addition would pass two 192-byte points
-// through local memory).  Row sums take stride_k = 1 (a thread streams K consecutive buckets of its row), column sums
-// stride_k = L (consecutive threads read consecutive buckets).  A tree of pairwise kernels needs log2 launches whose tails
-// are latency-bound; K = 16 per stage gives 3 fat launches per tree with the same number of additions (+7 %).
+// Both trees in two launches each, shaped for LATENCY as much as throughput (an XYZZ addition is ~9 us of dependent
+// multiplications, and the reduction sits on the critical path of every round: the host needs the commitments to draw the next
+// challenges).  Stage 1: one thread per (position, segment) adds K = 8 consecutive summands serially -- this is where the 2^19
+// buckets are read, one pass per axis.  Stage 2: one WARP per position folds the remaining len / 8 partials (strided loads, then a
+// 5-level tree through shared memory), rows and columns in the same launch.  Depth: 8 + <= 4 + 5 additions per tree (round 1's
+// pairwise kernels: 10 launches per tree; a 3-stage serial variant: 36 additions deep).
+//     stage 1: out[(g * ni + i) * nseg + s] = sum_{k < K} in[g * group_stride + (s * K + k) * stride_k + i * stride_i]
 template <class Fq>
 __global__ void __launch_bounds__(128) msm_segsum_kernel(const XYZZ<Fq>* __restrict__ in, XYZZ<Fq>* __restrict__ out, size_t groups, size_t nseg,
                                                          uint32_t K, size_t ni, size_t stride_k, size_t stride_i, size_t group_stride) {
   const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (t >= groups * nseg * ni) return;
-  const size_t i = t % ni, gs = t / ni, sg = gs % nseg, g = gs / nseg;
+  // thread order: position fastest for the column sums (stride_i == 1: coalesced), segment fastest for the row sums
+  size_t i, sg, g;
+  if (stride_i == 1) {
+    i = t % ni;
+    const size_t gs = t / ni;
+    sg = gs % nseg;
+    g = gs / nseg;
+  } else {
+    sg = t % nseg;
+    const size_t gi = t / nseg;
+    i = gi % ni;
+    g = gi / ni;
+  }
   const XYZZ<Fq>* p = in + g * group_stride + sg * K * stride_k + i * stride_i;
   XYZZ<Fq> acc = ld_words(p);
   for (uint32_t k = 1; k < K; k++) acc.add(ld_words(p + (size_t)k * stride_k));
-  st_words(out + t, acc);
+  st_words(out + (g * ni + i) * nseg + sg, acc);
+}
+// stage 2: out[pos] = sum_{s < nseg} in[pos * nseg + s] for two arrays at once (row partials then column partials)
+struct MsmFoldJob {
+  const void* in;
+  void* out;
+  size_t positions, nseg;
+};
+template <class Fq>
+__global__ void __launch_bounds__(128) msm_fold_kernel(MsmFoldJob a, MsmFoldJob b) {
+  __shared__ uint4 sm_raw[128 * sizeof(XYZZ<Fq>) / 16];
+  XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(sm_raw) + (threadIdx.x & ~31u);
+  const uint32_t lane = threadIdx.x & 31u;
+  size_t w = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const MsmFoldJob* job = &a;
+  if (w >= a.positions) {
+    w -= a.positions;
+    job = &b;
+  }
+  if (w >= job->positions) return;  // (whole warps leave together)
+  const XYZZ<Fq>* in = reinterpret_cast<const XYZZ<Fq>*>(job->in) + w * job->nseg;
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+  for (size_t k = lane; k < job->nseg; k += 32) g1_add(acc, ld_words(in + k));
+  sm[lane] = acc;
+  __syncwarp();
+  for (uint32_t s2 = 16; s2 >= 1; s2 >>= 1) {
+    if (lane < s2) {
+      XYZZ<Fq> t = sm[lane];
+      g1_add(t, sm[lane + s2]);
+      sm[lane] = t;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) st_words(reinterpret_cast<XYZZ<Fq>*>(job->out) + w, sm[0]);
 }
 // planes[j][p] for p in [0, nbits]: p < nbits -> sum of V[j][i] over i with bit p set; p == nbits -> sum of all.
+// Row planes (blockIdx.x <= rbits) and column planes in one launch.
 template <class Fq>
-__global__ void __launch_bounds__(256) msm_bitplane_kernel(const XYZZ<Fq>* v, size_t len, int nbits, XYZZ<Fq>* planes) {
+__global__ void __launch_bounds__(256) msm_bitplane_kernel(const XYZZ<Fq>* rsum, size_t R, int rbits, XYZZ<Fq>* rplanes, const XYZZ<Fq>* csum,
+                                                           size_t L, int cbits, XYZZ<Fq>* cplanes) {
   __shared__ uint4 sm_raw[256 * sizeof(XYZZ<Fq>) / 16];
   XYZZ<Fq>* sm = reinterpret_cast<XYZZ<Fq>*>(sm_raw);
-  const int p = blockIdx.x;
+  const bool rows = (int)blockIdx.x <= rbits;
+  const int p = rows ? blockIdx.x : blockIdx.x - (rbits + 1);
+  const int nbits = rows ? rbits : cbits;
+  const size_t len = rows ? R : L;
   const size_t j = blockIdx.y;
-  const XYZZ<Fq>* vec = v + j * len;
+  const XYZZ<Fq>* vec = (rows ? rsum : csum) + j * len;
   XYZZ<Fq> acc = XYZZ<Fq>::inf();
   for (size_t i = threadIdx.x; i < len; i += 256)
     if (p == nbits || ((i >> p) & 1)) g1_add(acc, ld_words(vec + i));
@@ -382,7 +433,7 @@ __global__ void __launch_bounds__(256) msm_bitplane_kernel(const XYZZ<Fq>* v, si
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) st_words(planes + j * (nbits + 1) + p, sm[0]);
+  if (threadIdx.x == 0) st_words((rows ? rplanes : cplanes) + j * (nbits + 1) + p, sm[0]);
 }
 struct MsmFinishJob {
   const void* extra;  // XYZZ[n_extra] further terms (hiding commitments, shifted parts)
@@ -522,11 +573,13 @@ __global__ void g1_canonical_kernel(const Affine<Fq>* in, size_t n, Affine<Fq>* 
 // ---- host driver ------------------------------------------------------------------------------
 template <class Fr, class Fq>
 int Msm<Fr, Fq>::pick_window(size_t n) {
-  // n = (base, scalar) pairs a typical MSM of this key gives ONE GPU.  Cost model: n * ceil(256 / c) mixed additions
-  // in the bucket pass + ~2.8 * 2^(c-1) for the reduction => c ~ log2(n) - 1, at most 20 (13 windows, 2^19 buckets).
+  // n = powers of this key resident on ONE GPU.  The bucket pass costs n * ceil(256 / c) additions per MSM, the reduction
+  // ~0.8 ns per bucket plus a latency floor; measured (profiles/r02_scaling_notes.md, 2^20-constraint proofs and their per-rank
+  // equivalents): c = 20 (13 windows, 2^19 buckets) wins from 2^21 powers per GPU on, c = 16 (16 windows, 2^15 buckets, a full
+  // top window) below that -- 4 and 8 GPUs on a 2^22-power key, or a single GPU on a small one -- and c ~ log2(n) - 1 for tiny keys.
   int lg = 0;
   while (((size_t)1 << (lg + 1)) <= n) lg++;
-  int c = lg - 1;
+  int c = lg >= 21 ? 20 : (lg >= 17 ? 16 : lg - 1);
   if (c < MSM_MIN_WINDOW) c = MSM_MIN_WINDOW;
   if (c > 20) c = 20;
   // The top window only holds what is left of the scalar: (BITS + 1) - (W - 1) c bits.  When that is a handful of bits
@@ -848,43 +901,23 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
   double units = 0;
   for (int j = 0; j < nj; j++) units += (double)jobs[j].n;
   size_t sp2 = cx.span_begin("msm_reduce", units);
-  DBuf<XYZZ<Fq>> ping(cx, (size_t)nj * B / 8 + 1), pong(cx, (size_t)nj * B / 64 + 1);
   DBuf<XYZZ<Fq>> rsum(cx, (size_t)nj * R), csum(cx, (size_t)nj * L);
-  // sums over `len` summands spaced `stride_k` apart for each of `ni` positions spaced `stride_i` apart, per job:
-  // stages of K <= 16 summands per thread until one value per position is left
-  auto reduce_axis = [&](size_t len, size_t ni, size_t stride_k, size_t stride_i, XYZZ<Fq>* result) {
-    const XYZZ<Fq>* cur = buckets.p;
-    size_t group_stride = B;
-    XYZZ<Fq>* bufs[2] = {ping.p, pong.p};
-    int which = 0;
-    if (len == 1) {
-      B2M_CUDA(cudaMemcpyAsync(result, cur, (size_t)nj * B * sizeof(XYZZ<Fq>), cudaMemcpyDeviceToDevice, cx.stream));
-      return;
-    }
-    while (len > 1) {
-      const uint32_t K = (uint32_t)std::min<size_t>(len, len > 16 && len < 64 ? 8 : 16);  // (keeps every stage's K >= 2)
-      const size_t nseg = len / K;
-      XYZZ<Fq>* out = nseg == 1 ? result : bufs[which];
-      const size_t threads = (size_t)nj * nseg * ni;
-      msm_segsum_kernel<Fq><<<div_up(threads, 128), 128, 0, cx.stream>>>(cur, out, (size_t)nj, nseg, K, ni, stride_k, stride_i, group_stride);
-      B2M_CHECK_LAUNCH();
-      cx.launches++;
-      // the stage's output is laid out [job][segment][position]: summands of a position are now `ni` apart
-      cur = out;
-      group_stride = nseg * ni;
-      stride_k = ni;
-      stride_i = 1;
-      len = nseg;
-      which ^= 1;
-    }
-  };
-  reduce_axis(L, R, 1, L, rsum.p);  // Rsum[hi] = sum_lo B[hi][lo]
-  reduce_axis(R, L, L, 1, csum.p);  // Csum[lo] = sum_hi B[hi][lo]
+  {
+    // stage 1: K summands per thread (K = 8, or the whole axis when it is shorter); stage 2: one warp per position
+    const uint32_t Kr = (uint32_t)std::min<size_t>(L, 8), Kc = (uint32_t)std::min<size_t>(R, 8);
+    const size_t seg_r = L / Kr, seg_c = R / Kc;  // partials per row / per column
+    DBuf<XYZZ<Fq>> part_r(cx, (size_t)nj * R * seg_r), part_c(cx, (size_t)nj * L * seg_c);
+    msm_segsum_kernel<Fq><<<div_up((size_t)nj * R * seg_r, 128), 128, 0, cx.stream>>>(buckets.p, part_r.p, (size_t)nj, seg_r, Kr, R, 1, L, B);
+    msm_segsum_kernel<Fq><<<div_up((size_t)nj * L * seg_c, 128), 128, 0, cx.stream>>>(buckets.p, part_c.p, (size_t)nj, seg_c, Kc, L, L, 1, B);
+    const MsmFoldJob fr{part_r.p, rsum.p, (size_t)nj * R, seg_r}, fc{part_c.p, csum.p, (size_t)nj * L, seg_c};
+    msm_fold_kernel<Fq><<<div_up(((size_t)nj * R + (size_t)nj * L) * 32, 128), 128, 0, cx.stream>>>(fr, fc);
+    B2M_CHECK_LAUNCH();
+    cx.launches += 3;
+  }
   DBuf<XYZZ<Fq>> rplanes(cx, (size_t)nj * (rbits + 1)), cplanes(cx, (size_t)nj * (cbits + 1));
-  msm_bitplane_kernel<Fq><<<dim3(rbits + 1, nj), 256, 0, cx.stream>>>(rsum.p, R, rbits, rplanes.p);
-  msm_bitplane_kernel<Fq><<<dim3(cbits + 1, nj), 256, 0, cx.stream>>>(csum.p, L, cbits, cplanes.p);
+  msm_bitplane_kernel<Fq><<<dim3(rbits + 1 + cbits + 1, nj), 256, 0, cx.stream>>>(rsum.p, R, rbits, rplanes.p, csum.p, L, cbits, cplanes.p);
   B2M_CHECK_LAUNCH();
-  cx.launches += 2;
+  cx.launches++;
   msm_finish_kernel<Fq><<<nj, 64, 0, cx.stream>>>(rplanes.p, rbits, cplanes.p, cbits, 1, fj);
   B2M_CHECK_LAUNCH();
   cx.launches++;
