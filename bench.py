@@ -286,7 +286,7 @@ def main():
     scalar_bits = 255 if args.curve == "bls12_381" else 254
     msm_windows, mul_peak = (scalar_bits + win_bits) // win_bits, None  # signed c-bit windows per scalar (c = 20 -> 13)
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_microbench_int_alu.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_microbench_int_alu.json")) as f:
             mb = json.load(f)
         mul_peak = max(v for k, v in mb.items() if k.startswith("fq_mul")) if args.curve == "bls12_381" else None
     except Exception:
@@ -295,12 +295,12 @@ def main():
     # addition 10; L levels leave 1/2^L of the references to the XYZZ kernel
     share = 0.5 ** aff_levels
     muls = msm_windows * (lev["units"] * ((1 - share) * 6 + share * 10) + (acc["units"] - lev["units"]) * 10)
-    traffic = None  # DRAM bytes per launch from the committed `ncu --set full` captures (profiles/), scaled to this run's mean launch
+    traffic = None  # DRAM bytes per launch from the committed `ncu --set full` capture of THIS round's kernels (profiles/), scaled to this run's mean launch
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
             tr = json.load(f)
         if args.curve == "bls12_381" and acc["launches"]:
-            per_pair = tr["levels"]["dram_bytes_per_pair"] if lev["launches"] else tr["dram_bytes_per_pair"]
+            per_pair = (tr["levels"]["dram_bytes_per_pair"] + tr["accumulate_after_levels"]["dram_bytes_per_pair"]) if lev["launches"] else tr["dram_bytes_per_pair"]
             traffic = per_pair * acc["units"] / acc["launches"]
     except Exception:
         pass
@@ -324,9 +324,9 @@ def main():
                      "algorithmic_bytes_per_launch": (acc["units"] * pair_bytes / acc["launches"]) if acc["launches"] else None,
                      "algorithmic_bytes_per_pair": pair_bytes, "launch": "the bucket pass of one MSM (mean over the proof's MSMs)",
                      "note": "bound by the 32-bit integer multiplier, not by HBM (roofline_int_alu; DESIGN.md Rooflines); traffic = "
-                             "level kernels only (profiles/r01_ncu_affine_levels.md)"},
+                             "level + accumulate kernels of one 2^22-pair MSM (profiles/r02_ncu_level_accumulate.md)"},
         # the meaningful roofline of these kernels: Fq multiplications per second against the whole-chip
-        # integer-multiply microbenchmark (profiles/r01_microbench_int_alu.json, tools/microbench.cu)
+        # integer-multiply microbenchmark (profiles/r02_microbench_int_alu.json, tools/microbench.cu)
         "roofline_int_alu": {"kernel": "MSM bucket pass", "unit": "G Fq multiplications/s",
                              "achieved": (muls / (bucket_ms / 1e3) / 1e9) if bucket_ms else None,
                              "peak": mul_peak, "frac": (muls / (bucket_ms / 1e3) / 1e9 / mul_peak) if bucket_ms and mul_peak else None,
