@@ -391,11 +391,18 @@ B2M_HD Affine<Fq> aff_add_slow(const Affine<Fq>& P, const Affine<Fq>& Q, uint32_
 //             ~27 k ALU instructions are spread over 5-6 warps per sub-partition instead of blocking a 128-168-register warp;
 //   PHASE 2 = addition pass only: every resident warp is inside multiplication code nearly all the time.
 // The chain inverse crosses in A.inv[t].
+//   PHASE 3 = denominator pass WITHOUT the inversion: the chain product goes to A.inv[t] and a separate kernel
+//             (msm_impl.cuh fq_batch_inverse_kernel) inverts all chain products of the level together -- a second level of
+//             Montgomery's trick across threads: one binary-Euclid inversion per 128 chains (8 192 additions) instead of one per
+//             chain, executed by one lane while the scan multiplications around it are warp-wide.
 template <class Fq, int PHASE, bool PIPE = true>
 B2M_HD void aff_level_thread_sp(const AffLevel<Fq>& A, const Affine<Fq>* base, uint32_t t) {
   const uint32_t total = B2M_AFF_LDG32(A.off_out + A.B);
   const AffMap mp = aff_map(A, t, total);
-  if (!mp.cnt) return;
+  if (!mp.cnt) {
+    if (PHASE == 3) B2M_AFF_ST(A.inv + t, Fq::one());  // (the batch inversion reads every slot)
+    return;
+  }
   const uint32_t cnt = mp.cnt;
   const size_t nth = A.nthreads;
   const uint4* meta = A.meta + t;
@@ -420,6 +427,10 @@ B2M_HD void aff_level_thread_sp(const AffLevel<Fq>& A, const Affine<Fq>* base, u
       const Fq den = aff_fast(w, c1, c2) ? d : Fq::one();
       B2M_AFF_ST(pref + (size_t)k * nth, run);
       run = run * den;
+    }
+    if (PHASE == 3) {
+      B2M_AFF_ST(A.inv + t, run);
+      return;
     }
     inv = run.inverse_fast();
     if (PHASE == 1) {

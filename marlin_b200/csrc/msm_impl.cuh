@@ -211,6 +211,54 @@ __global__ void __launch_bounds__(128, MINB) msm_affine_level_sp_kernel(const Af
   if (t < A.nthreads) aff_level_thread_sp<Fq, PHASE, PIPE>(A, base, t);
 }
 
+// v[i] <- 1 / v[i] for all i < n (no zero among them): Montgomery's trick in two levels -- 4 values per thread, a prefix and a
+// suffix product scan across the warp (shuffles), ONE inversion per warp (lane 31), back-substitution.  Used by the split level
+// kernels to invert all chain products of a level together.
+template <class Fq>
+__device__ __forceinline__ Fq shfl_fq(const Fq& a, int src_lane) {
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < Fq::N; i++) r.l[i] = __shfl_sync(0xffffffffu, a.l[i], src_lane);
+  return r;
+}
+template <class Fq>
+__global__ void __launch_bounds__(128) fq_batch_inverse_kernel(Fq* v, size_t n) {
+  constexpr int G = 4;
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const size_t i0 = t * G;
+  Fq e[G], pre[G];
+  Fq run = Fq::one();
+#pragma unroll
+  for (int k = 0; k < G; k++) {
+    e[k] = i0 + k < n ? ld_words(v + i0 + k) : Fq::one();
+    pre[k] = run;
+    run = run * e[k];
+  }
+  // inclusive prefix / suffix products of `run` across the warp
+  Fq pin = run, sin = run;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const Fq up = shfl_fq(pin, lane - d < 0 ? lane : lane - d);
+    const Fq dn = shfl_fq(sin, lane + d > 31 ? lane : lane + d);
+    if (lane >= d) pin = pin * up;
+    if (lane + d <= 31) sin = sin * dn;
+  }
+  Fq tinv = Fq::one();
+  if (lane == 31) tinv = fq_inverse(pin);  // 1 / (product of the warp's 128 values)
+  tinv = shfl_fq(tinv, 31);
+  Fq before = shfl_fq(pin, lane == 0 ? 0 : lane - 1), after = shfl_fq(sin, lane == 31 ? 31 : lane + 1);
+  if (lane == 0) before = Fq::one();
+  if (lane == 31) after = Fq::one();
+  Fq inv_run = tinv * before * after;  // 1 / (this thread's 4 values)
+#pragma unroll
+  for (int k = G - 1; k >= 0; k--) {
+    const Fq ek = inv_run * pre[k];
+    inv_run = inv_run * e[k];
+    if (i0 + k < n) st_words(v + i0 + k, ek);
+  }
+}
+
 // Partials are ordered by bucket (they follow the sorted references).  The first partial of each bucket
 // sums the ones that follow it and stores the bucket; a bucket cut into many partials (skewed scalar
 // distributions, e.g. a polynomial whose coefficients are nearly all equal) is queued for
@@ -829,6 +877,7 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
           //   4 (default), 5: fused kernel, loads at use, compiled for that many resident CTAs per SM; 3: operands prefetched (3 CTAs/SM)
           //   8, 9: fused, branch-free and software-pipelined addition pass (3 / 2 CTAs/SM)
           //   11-13: split -- denominator pass + inversion at 5 CTAs/SM, then the addition pass pipelined at 3 / 2 CTAs/SM or plain at 4
+          //   21, 22: split with ONE batch inversion of all chain products of the level between the passes
           const int variant = l == 0 ? affine_ctas : affine_ctas_upper;
           static const char* const lvl_names[MSM_MAX_AFFINE_LEVELS] = {"msm_aff_level0", "msm_aff_level1", "msm_aff_level2", "msm_aff_level3",
                                                                        "msm_aff_level4", "msm_aff_level5"};
@@ -844,6 +893,14 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
               else if (variant == 12) msm_affine_level_sp_kernel<Fq, 2, 2><<<grid, 128, 0, cx.stream>>>(A, base);
               else msm_affine_level_sp_kernel<Fq, 4, 2, false><<<grid, 128, 0, cx.stream>>>(A, base);
               cx.launches++;
+              break;
+            // split with the level-wide batch inversion between the two passes (21: plain addition pass at 4 CTAs/SM, 22: pipelined at 3)
+            case 21: case 22:
+              msm_affine_level_sp_kernel<Fq, 6, 3><<<grid, 128, 0, cx.stream>>>(A, base);
+              fq_batch_inverse_kernel<Fq><<<div_up(div_up(nthreads, 4), 128), 128, 0, cx.stream>>>(lvl_inv.p, nthreads);
+              if (variant == 21) msm_affine_level_sp_kernel<Fq, 4, 2, false><<<grid, 128, 0, cx.stream>>>(A, base);
+              else msm_affine_level_sp_kernel<Fq, 3, 2><<<grid, 128, 0, cx.stream>>>(A, base);
+              cx.launches += 2;
               break;
             default: msm_affine_level_kernel<Fq, 4, false><<<grid, 128, 0, cx.stream>>>(A, base); break;
           }

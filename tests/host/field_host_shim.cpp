@@ -85,6 +85,7 @@ static void run_levels(const uint32_t* tables, const uint32_t* refs, const uint3
       if (variant == 3) aff_level_thread_sp<Fq, 0>(A, base, t);
       else if (variant == 4) { aff_level_thread_sp<Fq, 1>(A, base, t); aff_level_thread_sp<Fq, 2>(A, base, t); }
       else if (variant == 5) { aff_level_thread_sp<Fq, 1>(A, base, t); aff_level_thread_sp<Fq, 2, false>(A, base, t); }
+      else if (variant == 6) { aff_level_thread_sp<Fq, 3>(A, base, t); invs[t] = invs[t].inverse_fast(); aff_level_thread_sp<Fq, 2, false>(A, base, t); }  // (the device inverts the level's chain products together)
       else if (T & 1) aff_level_thread<Fq, true>(A, base, t);
       else aff_level_thread<Fq, false>(A, base, t);
     }

@@ -151,7 +151,8 @@ def test_batched_affine_levels(hostlib, ci, curve):
         cases = [(0, 1, 0, 0), (1, 1, 0, 0), (1, 4, 0, 0), (2, 3, 0, 0), (3, 8, 0, 0), (7, 5, 0, 0), (3, 64, 0, 0),
                  (1, 1, 0, 1), (1, 4, 0, 1), (2, 3, 0, 1), (3, 2, 0, 1), (4, 1, 0, 1), (3, 8, 0, 1), (7, 5, 0, 1), (3, 64, 0, 1),
                  (1, 1, 3, 1), (1, 2, 3, 1), (2, 3, 3, 1), (3, 8, 3, 1), (4, 5, 3, 0), (7, 4, 3, 1), (3, 64, 3, 1),
-                 (1, 1, 4, 1), (2, 3, 4, 1), (3, 8, 4, 0), (3, 64, 4, 1), (1, 1, 5, 1), (2, 3, 5, 1), (3, 8, 5, 0), (3, 64, 5, 1)]
+                 (1, 1, 4, 1), (2, 3, 4, 1), (3, 8, 4, 0), (3, 64, 4, 1), (1, 1, 5, 1), (2, 3, 5, 1), (3, 8, 5, 0), (3, 64, 5, 1),
+                 (1, 1, 6, 1), (2, 3, 6, 1), (3, 8, 6, 0), (3, 16, 6, 1)]  # 6: split with the chain products inverted outside the thread function
         for levels, T, variant, interleaved in cases:
             out = np.zeros(B * 2 * n32, dtype=np.uint32)
             hostlib.affine_levels_host(ci, tab_l.ctypes.data_as(ctypes.c_void_p), refs_a.ctypes.data_as(ctypes.c_void_p),

@@ -213,6 +213,7 @@ def test_msm_skewed_scalars(b2m_ctx):
     (1, 1, 4, 4, 1), (2, 3, 4, 4, 1), (3, 64, 4, 4, 1), (4, 5, 3, 3, 1), (6, 2, 5, 5, 1),   # fused kernel variants, default (interleaved) mapping
     (3, 64, 8, 8, 1), (2, 3, 9, 9, 1), (4, 1, 9, 8, 0), (1, 7, 8, 8, 1),                    # software-pipelined kernels
     (3, 64, 11, 13, 1), (2, 3, 12, 11, 1), (4, 1, 13, 12, 0), (3, 5, 13, 11, 1), (1, 64, 12, 12, 1),  # split: two kernels per level
+    (3, 64, 21, 21, 1), (2, 3, 22, 21, 1), (4, 1, 21, 22, 0), (3, 16, 22, 22, 1), (1, 5, 21, 21, 1),          # split + level-wide batch inversion
     (3, 64, 4, 4, 0), (2, 5, 3, 5, 0)])                                                     # blocked mapping
 def test_msm_affine_levels_forced(b2m_ctx, monkeypatch, levels, T, variant, upper, mapping):
     """The batched-affine levels (csrc/msm_affine.cuh) are skipped for small MSMs; force them on (any size, odd
