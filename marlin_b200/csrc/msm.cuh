@@ -60,11 +60,14 @@ struct Msm {
   // Off for a 254-bit Fq: its multiplications are so cheap that the levels' extra memory traffic costs more
   // than the saved multiplications (BN254 2^20: 126.6 ms with, 120.6 ms without).
   int affine_levels = Fq::N > 8 ? 3 : 0;
-  int affine_ctas_upper = 4;  // the same for levels >= 1 (streaming operands); B2M_MSM_AFFINE_CTAS_UPPER
+  // levels >= 1 (streaming operands): split kernels with the level-wide batch inversion, 32 additions per chain -- measured
+  // 33.0 + 19.0 ms per 2^20 proof against 36.5 + 20.4 for the fused kernel at T = 64 (level 0 is the other way round: 77.7 vs 82.3)
+  int affine_ctas_upper = 21;  // B2M_MSM_AFFINE_CTAS_UPPER
   int affine_ctas = 4;      // level-kernel variant of level 0 (B2M_MSM_AFFINE_CTAS; the list is at the launch site in msm_impl.cuh)
   size_t affine_min_refs = MSM_AFFINE_MIN_REFS;  // B2M_MSM_AFFINE_MIN_REFS
   int affine_map = 1;       // output -> thread mapping of the levels: 1 = warp-interleaved (coalesced), 0 = blocked; B2M_MSM_AFFINE_MAP
-  int affine_T = 64;        // additions per thread and inversion in those levels; B2M_MSM_AFFINE_T
+  int affine_T = 64;        // additions per thread (chain) at level 0; B2M_MSM_AFFINE_T sets both
+  int affine_T_upper = 32;  // ... at levels >= 1; B2M_MSM_AFFINE_T_UPPER
   int acc_ctas_per_sm = 3;  // resident CTAs of msm_accumulate_kernel per SM (occupancy query)
   DBuf<Affine<Fq>> tables;  // [W][stride]:  tables[w * stride + k] = 2^(c*w) * P_(k * world + rank)
 

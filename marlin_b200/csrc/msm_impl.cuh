@@ -680,9 +680,9 @@ Msm<Fr, Fq>::Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, const Affine<
   B2M_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas_per_sm, msm_accumulate_kernel<Fq>, 128, 0));
   if (acc_ctas_per_sm < 1) acc_ctas_per_sm = 1;
   if (const char* e = getenv("B2M_MSM_AFFINE_LEVELS")) affine_levels = atoi(e);
-  if (const char* e = getenv("B2M_MSM_AFFINE_T")) affine_T = atoi(e);
+  if (const char* e = getenv("B2M_MSM_AFFINE_T")) affine_T = affine_T_upper = atoi(e);
+  if (const char* e = getenv("B2M_MSM_AFFINE_T_UPPER")) affine_T_upper = atoi(e);
   if (const char* e = getenv("B2M_MSM_AFFINE_CTAS")) affine_ctas = atoi(e);
-  affine_ctas_upper = affine_ctas;
   if (const char* e = getenv("B2M_MSM_AFFINE_CTAS_UPPER")) affine_ctas_upper = atoi(e);
   if (const char* e = getenv("B2M_MSM_AFFINE_MIN_REFS")) affine_min_refs = (size_t)atoll(e);
   if (const char* e = getenv("B2M_MSM_AFFINE_MAP")) affine_map = atoi(e);
@@ -691,6 +691,8 @@ Msm<Fr, Fq>::Msm(Ctx& cx, const Affine<Fq>* host_powers, size_t n, const Affine<
   if (affine_levels > MSM_MAX_AFFINE_LEVELS) affine_levels = MSM_MAX_AFFINE_LEVELS;
   if (affine_T < 1) affine_T = 1;
   if (affine_T > 1024) affine_T = 1024;
+  if (affine_T_upper < 1) affine_T_upper = 1;
+  if (affine_T_upper > 1024) affine_T_upper = 1024;
 }
 
 template <class Fr, class Fq>
@@ -806,10 +808,11 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
       if (LV > 1) lvl_pts[1] = DBuf<Affine<Fq>>(cx, bound[2]);
       lvl_off[0] = DBuf<uint32_t>(cx, B + 1); lvl_off[1] = DBuf<uint32_t>(cx, B + 1); lvl_cnt = DBuf<uint32_t>(cx, B + 1);
       lvl_refs = DBuf<uint2>(cx, bound[LV]);
-      const size_t slots_l0 = (size_t)affine_T * ((bound[1] + affine_T - 1) / affine_T + 128);  // >= T * nthreads for either mapping
+      const size_t T_max = (size_t)std::max(affine_T, affine_T_upper), T_min = (size_t)std::min(affine_T, affine_T_upper);
+      const size_t slots_l0 = T_max * ((bound[1] + T_max - 1) / T_max + 128);  // >= T * nthreads at every level, for either mapping
       lvl_meta = DBuf<uint4>(cx, slots_l0);
       lvl_pref = DBuf<Fq>(cx, slots_l0);
-      lvl_inv = DBuf<Fq>(cx, slots_l0 / affine_T + 1);
+      lvl_inv = DBuf<Fq>(cx, slots_l0 / T_min + 256);
     }
     buckets.zero();  // empty buckets are never written: all-zero XYZZ is the point at infinity
     cudaEvent_t ev_ready, ev_sorted[MSM_MAX_BATCH], ev_acc[MSM_MAX_BATCH];
@@ -864,9 +867,10 @@ void Msm<Fr, Fq>::run_batch(const MsmJob<Fr, Fq>* jobs_in, int nj) {
           cx.launches++;
           exclusive_scan_u32(cx, lvl_cnt.p, off_out, (size_t)B + 1);
           const uint32_t lane_step = affine_map ? 32u : 1u;
-          const uint32_t nthreads = (uint32_t)(lane_step * ((bound[l + 1] + (size_t)lane_step * affine_T - 1) / ((size_t)lane_step * affine_T)));
+          const size_t T_l = (size_t)(l == 0 ? affine_T : affine_T_upper);  // additions per thread (and per chain) at this level
+          const uint32_t nthreads = (uint32_t)(lane_step * ((bound[l + 1] + (size_t)lane_step * T_l - 1) / ((size_t)lane_step * T_l)));
           AffLevel<Fq> A{tables.p, stride, sorted[s].p, l > 0 ? lvl_pts[(l - 1) & 1].p : nullptr, off_in, off_out, B, lvl_pts[l & 1].p,
-                         l == LV - 1 ? lvl_refs.p : nullptr, lvl_pref.p, lvl_meta.p, (uint32_t)affine_T, nthreads, lane_step, lvl_inv.p};
+                         l == LV - 1 ? lvl_refs.p : nullptr, lvl_pref.p, lvl_meta.p, (uint32_t)T_l, nthreads, lane_step, lvl_inv.p};
           if (l == 0)
             msm_affine_plan_kernel<Fq, true><<<div_up(nthreads, 256), 256, 0, cx.stream>>>(A);
           else
