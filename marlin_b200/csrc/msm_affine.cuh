@@ -8,11 +8,17 @@
 // (Montgomery's trick): 6 field multiplications per addition instead of 10 for an XYZZ mixed addition.
 // A light plan pass resolves which two points make each output.  A thread then owns T outputs (warp-interleaved: the 32
 // lanes of a warp own 32 T consecutive outputs, so every step of a warp touches 32 adjacent outputs): pass 1 multiplies
-// the denominators up (prefix products to a scratch array), one binary-Euclid inversion (field.cuh inverse_fast: adds and
-// shifts only), pass 2 walks back and writes the sums.  Three forms of the arithmetic kernel are kept, all byte-identical
-// in their results (profiles/r02_level_kernel_notes.md has the measurements that chose the default): the fused kernel
-// (aff_level_thread), a branch-free software-pipelined one (aff_level_thread_sp) and the latter's split into two kernels.  After a few levels the remaining points
-// (n / 2^levels) go through the XYZZ bucket pass, which balances any bucket-size distribution.
+// the denominators up (prefix products to a scratch array), the chain product is inverted, pass 2 walks back and writes
+// the sums.  After a few levels the remaining points (n / 2^levels) go through the XYZZ bucket pass, which balances any
+// bucket-size distribution.
+//
+// Forms of the arithmetic kernel, all byte-identical in their results (profiles/r02_level_kernel_notes.md has the
+// measurements that chose the defaults):
+//   * fused (aff_level_thread): both passes and one binary-Euclid inversion (field.cuh inverse_fast) per thread -- the
+//     default for level 0, whose operands are random gathers from the window tables;
+//   * branch-free and software-pipelined (aff_level_thread_sp, PHASE 0);
+//   * split into two kernels (PHASE 1 + 2, or PHASE 3 + 2 with ONE batch inversion of all chain products of the level in
+//     between: msm_impl.cuh fq_batch_inverse_kernel) -- the default for the streaming levels >= 1.
 //
 // Host/device shared: tests/host builds this with g++ (carry flag emulated) and checks it against the oracle.
 #pragma once
