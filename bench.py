@@ -318,7 +318,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "constraints/s", "h2d_bytes_per_step": int(circ.instance.nbytes + circ.witness.nbytes),
                 "d2h_bytes_per_step": len(proof) + 15 * 96, "host_memory": "pinned"},
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "kernel": ("MSM bucket pass: msm_affine_level_kernel x%d + msm_accumulate_kernel" % aff_levels) if lev["launches"]
+        "roofline": {"bound": "hbm", "kernel": ("MSM bucket pass: %d batched-affine level kernels (fused level 0, split levels >= 1) + msm_accumulate_kernel" % aff_levels) if lev["launches"]
                      else "msm_accumulate_kernel", "achieved": achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                      "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_source": peak_kind,
                      "algorithmic_bytes_per_launch": (acc["units"] * pair_bytes / acc["launches"]) if acc["launches"] else None,
