@@ -289,3 +289,17 @@ def test_saved_proof_checker(tmp_path, curve):
     except (ValueError, AssertionError):
         ok = False  # the flipped byte can also make a compressed point undecodable
     assert not ok
+
+
+def test_compressed_g1_generator_known_answer():
+    """ark-serialize compressed form of the BLS12-381 G1 generator: x little-endian with the flags in the two top bits of the last
+    byte (bit 7 = y is the larger root, bit 6 = infinity) -- NOT the big-endian zcash encoding (whose first byte would be 0x97).
+    The hex string is the value arkworks prints for `G1Affine::prime_subgroup_generator()` (recalled published vector; the oracle's
+    format rules themselves are `[U]`)."""
+    from oracle import ec, transcript as T
+    from oracle.params import BLS12_381 as c
+    g = T.g1_compressed(c, c.g)
+    assert g.hex() == "bbc622db0af03afbef1a7af93fe8556c58ac1b173f3a4ea105b974974f8c68c30faca94f8c63952694d79731a7d3f117"
+    neg = T.g1_compressed(c, ec.affine_neg(c, c.g))
+    assert neg[:-1] == g[:-1] and neg[-1] == g[-1] | 0x80  # -G has the larger y
+    assert T.g1_compressed(c, None) == bytes(47) + bytes([0x40])
